@@ -1,0 +1,588 @@
+// c2ray_kernels.cuh -- CUDA kernels of the hot path (sm_100a).
+//   (a)+(b) k_sweep_shell : evolve_source.F90 do_source / evolve_point.F90 evolve0D / column_density.f90 cinterp /
+//                           radiation_photoionrates.f90 photoion_rates as a max-norm shell wavefront over many
+//                           sources at once: one launch per shell radius, every (active source, cell)
+//                           pair of that shell is one work item.
+//   (c)     k_global_pass : evolve_point.F90 evolve0D_global / do_chemistry + doric + thermal, one cell per thread,
+//                           HBM-streaming SoA loads/stores, warp-shuffle reductions for the convergence vote.
+//   tables  k_build_tables: radiation_tables.f90 spec_integration on the device.
+#pragma once
+#include <cuda_runtime.h>
+#include "c2ray_physics.cuh"
+
+namespace c2 {
+
+// ------------------------------------------------------------------------------------------------
+// Sweep bookkeeping
+// ------------------------------------------------------------------------------------------------
+struct Slot {          // one source being traced (evolve_source.F90:66-238 local state)
+  double nflux[3];     // NormFlux, NormFluxPL, NormFluxQPL of the source
+  double total_flux;   // :122-128
+  double loss;         // photon_loss_src
+  int src;             // 0-based source number
+  int s[3];            // srcpos (1-based mesh position)
+  int lo[3], hi[3];    // current sub-box reach: last_l = srcpos - lo, last_r = srcpos + hi (:143-144)
+  int nbox;
+  int active;
+};
+
+struct SweepTotals {
+  double photon_loss;               // photon_loss(1), evolve_source.F90:233
+  unsigned long long sum_nbox;      // :236
+  unsigned long long updates;       // evolve0D calls that did work
+  int nactive;
+  int pad;
+};
+
+struct SweepGeom {
+  int L[3], R[3];   // lastpos_l / lastpos_r reach (:103-105)
+  int subboxsize;
+  int cap;          // entries per species per shell buffer
+};
+
+__device__ __forceinline__ int shell_cells(int r) { return r == 0 ? 1 : 24 * r * r + 2; }
+
+// index of offset (di,dj,dk), max-norm r, in the face-ordered shell layout (also the thread order)
+__device__ __forceinline__ int shell_index(int di, int dj, int dk, int r) {
+  if (r == 0) return 0;
+  const int n1 = 2 * r + 1, n0 = 2 * r - 1;
+  if (dk == -r) return (dj + r) * n1 + (di + r);
+  if (dk == r) return n1 * n1 + (dj + r) * n1 + (di + r);
+  int base = 2 * n1 * n1;
+  if (dj == -r) return base + (dk + r - 1) * n1 + (di + r);
+  base += n0 * n1;
+  if (dj == r) return base + (dk + r - 1) * n1 + (di + r);
+  base += n0 * n1;
+  if (di == -r) return base + (dk + r - 1) * n0 + (dj + r - 1);
+  return base + n0 * n0 + (dk + r - 1) * n0 + (dj + r - 1);
+}
+__device__ __forceinline__ void shell_decode(int c, int r, int& di, int& dj, int& dk) {
+  if (r == 0) { di = dj = dk = 0; return; }
+  const int n1 = 2 * r + 1, n0 = 2 * r - 1;
+  const int fz = n1 * n1, fy = n0 * n1, fx = n0 * n0;
+  if (c < 2 * fz) {
+    const int f = c >= fz; c -= f * fz;
+    dk = f ? r : -r; dj = c / n1 - r; di = c % n1 - r;
+  } else if ((c -= 2 * fz) < 2 * fy) {
+    const int f = c >= fy; c -= f * fy;
+    dj = f ? r : -r; dk = c / n1 - r + 1; di = c % n1 - r;
+  } else {
+    c -= 2 * fy;
+    const int f = c >= fx; c -= f * fx;
+    di = f ? r : -r; dk = c / n0 - r + 1; dj = c % n0 - r + 1;
+  }
+}
+
+__device__ __forceinline__ int wrap0(int p1, int n) {  // 1-based unwrapped -> 0-based periodic (modulo(p-1,n))
+  int m = (p1 - 1) % n;
+  return m < 0 ? m + n : m;
+}
+
+__global__ void k_slots_init(Slot* slots, int nslots, const int* __restrict__ src_ids, const int* __restrict__ srcpos,
+                             const double* __restrict__ nf, const double* __restrict__ nfpl,
+                             const double* __restrict__ nfqpl, SweepTotals* tot, int* active_list) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) tot->nactive = nslots;
+  if (t >= nslots) return;
+  Slot s;
+  const int ns = src_ids[t];
+  s.src = ns;
+  for (int d = 0; d < 3; d++) { s.s[d] = srcpos[3 * ns + d]; s.lo[d] = 0; s.hi[d] = 0; }
+  s.nflux[0] = nf[ns];
+  s.nflux[1] = (d_run.sed[1].hi >= d_run.sed[1].lo && nfpl) ? nfpl[ns] : 0.0;
+  s.nflux[2] = (d_run.sed[2].hi >= d_run.sed[2].lo && nfqpl) ? nfqpl[ns] : 0.0;
+  double tf = s.nflux[0] * d_run.sed[0].S_star;                       // evolve_source.F90:122
+  if (d_run.sed[1].hi >= d_run.sed[1].lo) tf = tf + s.nflux[1] * d_run.sed[1].S_star;  // :124
+  if (d_run.sed[2].hi >= d_run.sed[2].lo) tf = tf + s.nflux[2] * d_run.sed[2].S_star;  // :127
+  s.total_flux = tf;
+  s.loss = tf;  // :129
+  s.nbox = 0;
+  s.active = 1;
+  slots[t] = s;
+  active_list[t] = t;
+}
+
+// The `do while` test of evolve_source.F90:136-144 for every slot, then compaction of the active slots.
+// Single block.
+__global__ void k_decide(Slot* slots, int nslots, SweepGeom g, SweepTotals* tot, int* active_list) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < nslots; t += blockDim.x) {
+    Slot& s = slots[t];
+    if (!s.active) continue;
+    const bool go = s.loss > loss_fraction * s.total_flux && s.hi[2] < g.R[2] && s.lo[2] < g.L[2];
+    if (go) {
+      s.nbox = s.nbox + 1;
+      s.loss = 0.0;
+      for (int d = 0; d < 3; d++) {
+        s.hi[d] = min(g.subboxsize * s.nbox, g.R[d]);
+        s.lo[d] = min(g.subboxsize * s.nbox, g.L[d]);
+      }
+      active_list[atomicAdd(&cnt, 1)] = t;
+    } else {
+      s.active = 0;
+      atomicAdd(&tot->photon_loss, s.loss);                             // :233
+      atomicAdd(&tot->sum_nbox, (unsigned long long)s.nbox);            // :236
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) tot->nactive = cnt;
+}
+
+struct GridPtrs {
+  const double* ndens;
+  const double* xh_av;    // (N3,0:1)
+  const double* xhe_av;   // (N3,0:2)
+  double* rates;          // phih | phihe0 | phihe1 | phiheat, N3 each
+  size_t N3;
+};
+
+// One shell radius r of every active source.  Work item = (active slot, cell of the shell).
+__global__ void __launch_bounds__(128)
+k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot, SweepGeom g,
+              GridPtrs G, double* __restrict__ scratch, int r) {
+  const int nact = tot->nactive;
+  const int ncell = shell_cells(r);
+  const long long total = (long long)nact * ncell;
+  const size_t slot_stride = (size_t)6 * g.cap;                 // [parity][species][cap]
+  const int par = r & 1;
+  const bool iso = d_run.isothermal != 0;
+  const int m0 = d_run.mesh[0], m1 = d_run.mesh[1], m2 = d_run.mesh[2];
+  unsigned int done = 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(t / ncell);
+    const int c = (int)(t - (long long)a * ncell);
+    const int sid = active_list[a];
+    Slot& S = slots[sid];
+    int di, dj, dk;
+    shell_decode(c, r, di, dj, dk);
+    if (di < -S.lo[0] || di > S.hi[0] || dj < -S.lo[1] || dj > S.hi[1] || dk < -S.lo[2] || dk > S.hi[2]) continue;
+    double* cur = scratch + sid * slot_stride + (size_t)par * 3 * g.cap;
+    const double* prev = scratch + sid * slot_stride + (size_t)(par ^ 1) * 3 * g.cap;
+
+    const int i0 = S.s[0], j0 = S.s[1], k0 = S.s[2];
+    const size_t p = (size_t)wrap0(i0 + di, m0) + (size_t)m0 * ((size_t)wrap0(j0 + dj, m1) + (size_t)m1 * wrap0(k0 + dk, m2));
+    const double ndens_p = G.ndens[p];
+    const double h_av0 = fmax(G.xh_av[p], epsilon);
+    const double h_av1 = iso ? 0.0 : fmax(G.xh_av[p + G.N3], epsilon);
+    const double he_av0 = fmax(G.xhe_av[p], epsilon);
+    const double he_av1 = fmax(G.xhe_av[p + G.N3], epsilon);
+
+    double cin_H, cin_He0, cin_He1, path, vol_ph;
+    if (r == 0) {  // evolve_point.F90:140-150
+      cin_H = 0.0; cin_He0 = 0.0; cin_He1 = 0.0;
+      path = FL(0.5f) * d_run.dr[0];
+      vol_ph = d_run.dr[0] * d_run.dr[1] * d_run.dr[2];
+    } else {
+      // ---- cinterp, column_density.f90:28-345.  The geometric part must not be contracted into FMAs: the
+      // weights of not-yet-computed same-shell corners are exactly 0 only in plain IEEE mul/add.
+      const int ia = abs(di), ja = abs(dj), ka = abs(dk);
+      const int sgi = di >= 0 ? 1 : -1, sgj = dj >= 0 ? 1 : -1, sgk = dk >= 0 ? 1 : -1;
+      const double ddi = (double)di, ddj = (double)dj, ddk = (double)dk;
+      // dominant axis: z if ka>=ja&&ka>=ia ; else y if ja>=ia&&ja>=ka ; else x
+      int ax;  // 2=z 1=y 0=x
+      if (ka >= ja && ka >= ia) ax = 2; else if (ja >= ia && ja >= ka) ax = 1; else ax = 0;
+      // generic (u,v) transverse coordinates; w the dominant one
+      int du, dv, dw, sgu, sgv, sgw, u0, v0;
+      double fu, fv, fw;
+      if (ax == 2) { du = di; dv = dj; dw = dk; sgu = sgi; sgv = sgj; sgw = sgk; u0 = i0; v0 = j0; fu = ddi; fv = ddj; fw = ddk; }
+      else if (ax == 1) { du = di; dv = dk; dw = dj; sgu = sgi; sgv = sgk; sgw = sgj; u0 = i0; v0 = k0; fu = ddi; fv = ddk; fw = ddj; }
+      else { du = dj; dv = dk; dw = di; sgu = sgj; sgv = sgk; sgw = sgi; u0 = j0; v0 = k0; fu = ddj; fv = ddk; fw = ddi; }
+      // alam=(real(wm-w0)+sgw*0.5)/dw with wm-w0 = dw-sgw  (values exact in binary32)
+      const double alam = __ddiv_rn((double)((float)(dw - sgw) + (float)sgw * 0.5f), fw);
+      const double uc = __dadd_rn(__dmul_rn(alam, fu), (double)u0);
+      const double vc = __dadd_rn(__dmul_rn(alam, fv), (double)v0);
+      const double um = (double)((float)(u0 + du - sgu) + 0.5f * (float)sgu);
+      const double vm = (double)((float)(v0 + dv - sgv) + 0.5f * (float)sgv);
+      const double du_ = __dmul_rn(2.0, fabs(__dsub_rn(uc, um)));
+      const double dv_ = __dmul_rn(2.0, fabs(__dsub_rn(vc, vm)));
+      // weights: z-plane: s1=(1-dx)(1-dy) s2=(1-dy)dx s3=(1-dx)dy s4=dx dy  with (u,v)=(x,y)
+      //          y-plane: s1=(1-dx)(1-dz) s2=(1-dz)dx s3=(1-dx)dz s4=dx dz  with (u,v)=(x,z)
+      //          x-plane: s1=(1-dz)(1-dy) s2=(1-dz)dy s3=(1-dy)dz s4=dy dz  with (u,v)=(y,z): c2<->u-shifted
+      const double omu = __dsub_rn(1.0, du_), omv = __dsub_rn(1.0, dv_);
+      double s1, s2, s3, s4;
+      if (ax == 0) { s1 = __dmul_rn(omv, omu); s2 = __dmul_rn(omv, du_); s3 = __dmul_rn(omu, dv_); s4 = __dmul_rn(du_, dv_); }
+      else { s1 = __dmul_rn(omu, omv); s2 = __dmul_rn(omv, du_); s3 = __dmul_rn(omu, dv_); s4 = __dmul_rn(du_, dv_); }
+      // corner offsets: c1=(um,vm) c2=(u,vm) c3=(um,v) c4=(u,v), all at w-sgw
+      const int rm = r - 1;
+      int o1[3], o2[3], o3[3], o4[3];
+      {
+        const int uu = du, um_i = du - sgu, vv = dv, vm_i = dv - sgv, wm_i = dw - sgw;
+        int A[4][3];
+        const int cu[4] = {um_i, uu, um_i, uu}, cv[4] = {vm_i, vm_i, vv, vv};
+        for (int q = 0; q < 4; q++) {
+          if (ax == 2) { A[q][0] = cu[q]; A[q][1] = cv[q]; A[q][2] = wm_i; }
+          else if (ax == 1) { A[q][0] = cu[q]; A[q][2] = cv[q]; A[q][1] = wm_i; }
+          else { A[q][1] = cu[q]; A[q][2] = cv[q]; A[q][0] = wm_i; }
+        }
+        for (int d = 0; d < 3; d++) { o1[d] = A[0][d]; o2[d] = A[1][d]; o3[d] = A[2][d]; o4[d] = A[3][d]; }
+      }
+      double cH[4], cHe0[4], cHe1[4];
+      const int* oo[4] = {o1, o2, o3, o4};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int* o = oo[q];
+        const int nr = max(abs(o[0]), max(abs(o[1]), abs(o[2])));
+        if (nr == rm) {
+          const int id = shell_index(o[0], o[1], o[2], rm);
+          cH[q] = prev[id]; cHe0[q] = prev[g.cap + id]; cHe1[q] = prev[2 * g.cap + id];
+        } else {  // same-shell corner: its weight is exactly zero, the reference reads 0 or a finite value
+          cH[q] = 0.0; cHe0[q] = 0.0; cHe1[q] = 0.0;
+        }
+      }
+      const double sw[4] = {s1, s2, s3, s4};
+      double num, den;
+      num = 0.0; den = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf(cH[q], sigma_HI_at_ion_freq); num += cH[q] * w; den += w; }
+      cin_H = num / den;
+      num = 0.0; den = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf(cHe0[q], sigma_HeI_at_ion_freq); num += cHe0[q] * w; den += w; }
+      cin_He0 = num / den;
+      num = 0.0; den = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf(cHe1[q], sigma_HeII_at_ion_freq); num += cHe1[q] * w; den += w; }
+      cin_He1 = num / den;
+      const int wa = abs(dw), ua = abs(du), va = abs(dv);
+      if (wa == 1 && (ua == 1 || va == 1)) {  // :174-184
+        const double f = (ua == 1 && va == 1) ? sqrt3 : sqrt2;
+        cin_H = f * cin_H; cin_He0 = f * cin_He0; cin_He1 = f * cin_He1;
+      }
+      path = sqrt((fu * fu + fv * fv) / (fw * fw) + 1.0);  // :194
+      path = path * d_run.dr[0];                            // evolve_point.F90:158
+      const double xs = d_run.dr[0] * ddi, ys = d_run.dr[1] * ddj, zs = d_run.dr[2] * ddk;
+      const double dist2 = xs * xs + ys * ys + zs * zs;
+      vol_ph = FL(4.0f) * pi * dist2 * path;                // :168
+    }
+    // evolve_point.F90:237-244
+    const double cout_H = cin_H + h_av0 * ndens_p * path * (1.0 - abu_he);
+    const double cout_He0 = cin_He0 + he_av0 * ndens_p * path * abu_he;
+    const double cout_He1 = cin_He1 + he_av1 * ndens_p * path * abu_he;
+    cur[c] = cout_H; cur[g.cap + c] = cout_He0; cur[2 * g.cap + c] = cout_He1;
+
+    PhotOut phi = {0, 0, 0, 0, 0, 0};
+    if (cin_H < max_coldensh) {  // :250-270
+      phi = photoion_rates(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, vol_ph, S.nflux, h_av1);
+      phi.photo_HI = phi.photo_HI / (h_av0 * ndens_p * (1.0 - abu_he));
+      phi.photo_HeI = phi.photo_HeI / (he_av0 * ndens_p * abu_he);
+      phi.photo_HeII = phi.photo_HeII / (he_av1 * ndens_p * abu_he);
+    }
+    atomicAdd(G.rates + p, phi.photo_HI);                // :299-306
+    atomicAdd(G.rates + G.N3 + p, phi.photo_HeI);
+    atomicAdd(G.rates + 2 * G.N3 + p, phi.photo_HeII);
+    if (!iso) atomicAdd(G.rates + 3 * G.N3 + p, phi.heat);
+    // :310-314 photon loss over the current sub-box boundary
+    if (di == -S.lo[0] || dj == -S.lo[1] || dk == -S.lo[2] || di == S.hi[0] || dj == S.hi[1] || dk == S.hi[2])
+      atomicAdd(&S.loss, phi.photo_out * d_run.vol / vol_ph);
+    done++;
+  }
+  __syncwarp();
+  done = __reduce_add_sync(0xffffffffu, done);
+  if ((threadIdx.x & 31) == 0 && done) atomicAdd(&tot->updates, (unsigned long long)done);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (c) global pass: evolve_point.F90:325-440 evolve0D_global
+// ------------------------------------------------------------------------------------------------
+struct ChemPtrs {
+  const double* ndens;
+  const double* xh;      // (N3,0:1)   start-of-step state (frozen)
+  const double* xhe;     // (N3,0:2)
+  double* xh_av;         // (N3,0:1)
+  double* xhe_av;        // (N3,0:2)
+  double* xh_int;        // (N3,0:1)
+  double* xhe_int;       // (N3,0:2)
+  float* temp;           // (N3,0:2) real(si)
+  const double* rates;   // phih | phihe0 | phihe1 | phiheat
+  size_t N3;
+};
+struct ChemTotals {
+  int conv_flag;
+  int nit_max;
+  unsigned long long nit_total;
+};
+
+__global__ void __launch_bounds__(128)
+k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out) {
+  const size_t N3 = P.N3;
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool iso = d_run.isothermal != 0;
+  int vote = 0, nit = 0;
+  if (p < N3) {
+    Ion ion;
+    // evolve_point.F90:368-378.  Only the live members are loaded: ion%h(1), ion%he(2) are
+    // overwritten by doric before any use and ion%h_old(0), ion%he_old(0) are never read.
+    ion.h0 = fmax(epsilon, P.xh_int[p]);
+    ion.he0 = fmax(epsilon, P.xhe_int[p]);
+    ion.he1 = fmax(epsilon, P.xhe_int[p + N3]);
+    ion.h1 = 0.0; ion.he2 = 0.0;
+    ion.h_old0 = 0.0; ion.he_old0 = 0.0;
+    ion.h_old1 = fmax(epsilon, P.xh[p + N3]);
+    ion.he_old1 = fmax(epsilon, P.xhe[p + N3]);
+    ion.he_old2 = fmax(epsilon, P.xhe[p + 2 * N3]);
+    const double yh0_av_old = P.xh_av[p], yh1 = P.xh_av[p + N3];
+    const double yhe0_av_old = P.xhe_av[p], yhe1 = P.xhe_av[p + N3], yhe2_av_old = P.xhe_av[p + 2 * N3];
+    ion.h_av0 = fmax(epsilon, yh0_av_old); ion.h_av1 = fmax(epsilon, yh1);
+    ion.he_av0 = fmax(epsilon, yhe0_av_old); ion.he_av1 = fmax(epsilon, yhe1); ion.he_av2 = fmax(epsilon, yhe2_av_old);
+    const double n = P.ndens[p];
+    double temp_av_old, temper_old;
+    if (iso) { temp_av_old = d_run.temper_val; temper_old = d_run.temper_val; }
+    else { temp_av_old = (double)P.temp[p + N3]; temper_old = (double)P.temp[p + 2 * N3]; }
+    const double phiHI = P.rates[p], phiHeI = P.rates[N3 + p], phiHeII = P.rates[2 * N3 + p];
+    const double heat = iso ? 0.0 : P.rates[3 * N3 + p];
+    RecCol rc;
+    if (iso) ini_rec_colion_factors(d_run.temper_val, rc);  // mat_ini_test.F90:168
+    double avg_temper = temp_av_old, temper1;
+    nit = do_chemistry(dt, n, ion, phiHI, phiHeI, phiHeII, heat, temper_old, avg_temper, temper1, rc);
+    double temp_av_new = temp_av_old;
+    if (!iso) {  // set_temperature_point: stored as real(si), read back as such (:404)
+      const float t0 = (float)temper1, t1 = (float)avg_temper;
+      P.temp[p] = t0; P.temp[p + N3] = t1;
+      temp_av_new = (double)t1;
+    }
+    // :406-424
+    const double mfc = minimum_fractional_change, mfa = minimum_fraction_of_atoms;
+    if ((fabs(ion.h_av0 - yh0_av_old) > mfc && fabs((ion.h_av0 - yh0_av_old) / ion.h_av0) > mfc && ion.h_av0 > mfa) ||
+        (fabs(ion.he_av0 - yhe0_av_old) > mfc && fabs((ion.he_av0 - yhe0_av_old) / ion.he_av0) > mfc && ion.he_av0 > mfa) ||
+        (fabs(ion.he_av2 - yhe2_av_old) > mfc && fabs((ion.he_av2 - yhe2_av_old) / ion.he_av2) > mfc && ion.he_av2 > mfa) ||
+        ((fabs((temp_av_old - temp_av_new) / temp_av_new) > 1.0e-1) && (fabs(temp_av_new - temp_av_old) > 100.0)))
+      vote = 1;
+    P.xh_int[p] = ion.h0; P.xh_int[p + N3] = ion.h1;
+    P.xh_av[p] = ion.h_av0; P.xh_av[p + N3] = ion.h_av1;
+    P.xhe_int[p] = ion.he0; P.xhe_int[p + N3] = ion.he1; P.xhe_int[p + 2 * N3] = ion.he2;
+    P.xhe_av[p] = ion.he_av0; P.xhe_av[p + N3] = ion.he_av1; P.xhe_av[p + 2 * N3] = ion.he_av2;
+    if (nit_out) nit_out[p] = nit;
+  }
+  const unsigned int v = __reduce_add_sync(0xffffffffu, (unsigned)vote);
+  const unsigned int ns = __reduce_add_sync(0xffffffffu, (unsigned)nit);
+  const unsigned int nm = __reduce_max_sync(0xffffffffu, (unsigned)nit);
+  if ((threadIdx.x & 31) == 0) {
+    if (v) atomicAdd(&tot->conv_flag, (int)v);
+    atomicAdd(&tot->nit_total, (unsigned long long)ns);
+    atomicMax(&tot->nit_max, (int)nm);
+  }
+}
+
+// photonstatistics.f90:117-147 / :208-247 : sum_p ndens*x for 5 species
+__global__ void k_state_sums(const double* __restrict__ ndens, const double* __restrict__ xh, const double* __restrict__ xhe,
+                             size_t N3, double* out5) {
+  double s[5] = {0, 0, 0, 0, 0};
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N3; p += (size_t)gridDim.x * blockDim.x) {
+    const double n = ndens[p];
+    s[0] += n * xh[p]; s[1] += n * xh[p + N3];
+    s[2] += n * xhe[p]; s[3] += n * xhe[p + N3]; s[4] += n * xhe[p + 2 * N3];
+  }
+  __shared__ double sh[5][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int q = 0; q < 5; q++) {
+    double v = s[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[q][w] = v;
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int q = 0; q < 5; q++) {
+      double v = lane < nw ? sh[q][lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(out5 + q, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fine-grained parity hooks
+// ------------------------------------------------------------------------------------------------
+__global__ void k_photoion_batch(int n, const double* __restrict__ col6, const double* __restrict__ vol, double nf0,
+                                 double nf1, double nf2, const double* __restrict__ i_state, double* __restrict__ out6) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double* q = col6 + 6 * (size_t)t;
+  const double nflux[3] = {nf0, nf1, nf2};
+  const PhotOut r = photoion_rates(q[0], q[1], q[2], q[3], q[4], q[5], vol[t], nflux, i_state[t]);
+  double* o = out6 + 6 * (size_t)t;
+  o[0] = r.photo_HI; o[1] = r.photo_HeI; o[2] = r.photo_HeII; o[3] = r.heat; o[4] = r.photo_in; o[5] = r.photo_out;
+}
+
+__global__ void k_chemistry_batch(int n, double dt, const double* __restrict__ ndens, double* __restrict__ ion15,
+                                  const double* __restrict__ phi4, double* __restrict__ T3, int* __restrict__ nit_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double* v = ion15 + 15 * (size_t)t;
+  Ion ion;
+  ion.h0 = v[0]; ion.h1 = v[1]; ion.he0 = v[2]; ion.he1 = v[3]; ion.he2 = v[4];
+  ion.h_av0 = v[5]; ion.h_av1 = v[6]; ion.he_av0 = v[7]; ion.he_av1 = v[8]; ion.he_av2 = v[9];
+  ion.h_old0 = v[10]; ion.h_old1 = v[11]; ion.he_old0 = v[12]; ion.he_old1 = v[13]; ion.he_old2 = v[14];
+  RecCol rc;
+  if (d_run.isothermal) ini_rec_colion_factors(d_run.temper_val, rc);
+  double avg = T3[3 * t + 1], t1;
+  const int nit = do_chemistry(dt, ndens[t], ion, phi4[4 * t], phi4[4 * t + 1], phi4[4 * t + 2], phi4[4 * t + 3],
+                               T3[3 * t + 2], avg, t1, rc);
+  T3[3 * t] = t1; T3[3 * t + 1] = avg;
+  v[0] = ion.h0; v[1] = ion.h1; v[2] = ion.he0; v[3] = ion.he1; v[4] = ion.he2;
+  v[5] = ion.h_av0; v[6] = ion.h_av1; v[7] = ion.he_av0; v[8] = ion.he_av1; v[9] = ion.he_av2;
+  nit_out[t] = nit;
+}
+
+__global__ void k_rec_colion_batch(int n, const double* __restrict__ T, double* __restrict__ out12) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  RecCol r;
+  ini_rec_colion_factors(T[t], r);
+  double* o = out12 + 12 * (size_t)t;
+  o[0] = r.arech0; o[1] = r.brech0; o[2] = r.areche0; o[3] = r.breche0; o[4] = r.oreche0; o[5] = r.areche1;
+  o[6] = r.breche1; o[7] = r.treche1; o[8] = r.colli_HI; o[9] = r.colli_HeI; o[10] = r.colli_HeII; o[11] = r.v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// radiation_tables.f90:172-422 spec_integration on the device.  One block per (tau index, band).
+// ------------------------------------------------------------------------------------------------
+struct TableBuild {
+  double freq_min[NumFreqBnd], delta_freq[NumFreqBnd], plidx[NumFreqBnd];  // per band; plidx = index used for the band
+  double romw[NumFreq + 1];
+  double R_star2, h_over_kT;
+  double scaling[3], index[3];  // [1],[2]: pl, qpl
+  int active[3];
+  int isothermal;
+  double* photo_thick[3];
+  double* photo_thin[3];
+  double* heat_thick[3];
+  double* heat_thin[3];
+};
+
+__global__ void __launch_bounds__(128) k_build_tables(const TableBuild* __restrict__ tb) {
+  const int it = blockIdx.x;      // 0..NumTau
+  const int q = blockIdx.y;       // band 0..46
+  const int b = q + 1;
+  const double tau = it == 0 ? 0.0 : pow(FL(10.0f), minlogtau + dlogtau * (double)(it - 1));
+  const int nsp = (b <= NumBndin1) ? 1 : (b <= NumBndin1 + NumBndin2 ? 2 : 3);
+  const int hcol0 = (b <= NumBndin1) ? 0 : (b <= NumBndin1 + NumBndin2 ? 2 * b - NumBndin1 - 2 : 3 * b - NumBndin2 - NumBndin1 * 2 - 3);
+  const double ionf[3] = {ion_freq_HI, ion_freq_HeI, ion_freq_HeII};
+  const double w = tb->delta_freq[q];
+  __shared__ double red[4][8];
+  for (int s = 0; s < 3; s++) {
+    if (!tb->active[s]) continue;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // thick, thin, heat thick x3, heat thin x3
+    for (int x = threadIdx.x; x <= NumFreq; x += blockDim.x) {
+      const double f = tb->freq_min[q] + tb->delta_freq[q] * (double)x;
+      const double cs = pow(f / tb->freq_min[q], -tb->plidx[q]);
+      double thick = 0.0, thin = 0.0;
+      if (tau * cs < FL(700.0f)) {
+        if (s == 0) {
+          if (f * tb->h_over_kT < FL(700.0f)) {
+            const double base = 4.0 * pi * tb->R_star2 * two_pi_over_c_square * f * f;
+            const double ex = exp(-tau * cs), den = exp(f * tb->h_over_kT) - 1.0;
+            thick = base * ex / den;
+            thin = base * cs * ex / den;
+          }
+        } else {
+          const double pw = tb->scaling[s] * pow(f, -tb->index[s]);
+          const double ex = exp(-tau * cs);
+          thick = pw * ex;
+          thin = pw * cs * ex;
+        }
+      }
+      const double wr = w * tb->romw[x];
+      acc[0] += thick * wr; acc[1] += thin * wr;
+      if (!tb->isothermal)
+        for (int sp = 0; sp < nsp; sp++) {
+          const double e = hplanck * (f - ionf[sp]);
+          acc[2 + sp] += e * thick * wr; acc[5 + sp] += e * thin * wr;
+        }
+    }
+    // block reduction
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (int k = 0; k < 8; k++) {
+      double v = acc[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) red[wp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      const int k = threadIdx.x;
+      const double v = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+      const size_t o = (size_t)q * (NumTau + 1) + it;
+      if (k == 0) tb->photo_thick[s][o] = v;
+      else if (k == 1) tb->photo_thin[s][o] = v;
+      else if (!tb->isothermal) {
+        const int sp = (k - 2) % 3;
+        if (sp < nsp) {
+          const size_t ho = (size_t)(hcol0 + sp) * (NumTau + 1) + it;
+          if (k < 5) tb->heat_thick[s][ho] = v; else tb->heat_thin[s][ho] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// cinterp against a full-grid scratch (parity hook for column_density.f90:28; the sweep kernel carries the same
+// arithmetic on its shell buffers)
+__global__ void k_cinterp_batch(int n, const int* __restrict__ pos, int i0, int j0, int k0,
+                                const double* __restrict__ cdh, const double* __restrict__ cdhe, size_t N3,
+                                double* __restrict__ out4) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int m0 = d_run.mesh[0], m1 = d_run.mesh[1], m2 = d_run.mesh[2];
+  const int i = pos[3 * t], j = pos[3 * t + 1], k = pos[3 * t + 2];
+  const int di = i - i0, dj = j - j0, dk = k - k0;
+  const int ia = abs(di), ja = abs(dj), ka = abs(dk);
+  const int sgi = di >= 0 ? 1 : -1, sgj = dj >= 0 ? 1 : -1, sgk = dk >= 0 ? 1 : -1;
+  int ax;
+  if (ka >= ja && ka >= ia) ax = 2; else if (ja >= ia && ja >= ka) ax = 1; else ax = 0;
+  int du, dv, dw, sgu, sgv, sgw, u0, v0;
+  if (ax == 2) { du = di; dv = dj; dw = dk; sgu = sgi; sgv = sgj; sgw = sgk; u0 = i0; v0 = j0; }
+  else if (ax == 1) { du = di; dv = dk; dw = dj; sgu = sgi; sgv = sgk; sgw = sgj; u0 = i0; v0 = k0; }
+  else { du = dj; dv = dk; dw = di; sgu = sgj; sgv = sgk; sgw = sgi; u0 = j0; v0 = k0; }
+  const double fu = (double)du, fv = (double)dv, fw = (double)dw;
+  const double alam = __ddiv_rn((double)((float)(dw - sgw) + (float)sgw * 0.5f), fw);
+  const double uc = __dadd_rn(__dmul_rn(alam, fu), (double)u0);
+  const double vc = __dadd_rn(__dmul_rn(alam, fv), (double)v0);
+  const double um = (double)((float)(u0 + du - sgu) + 0.5f * (float)sgu);
+  const double vm = (double)((float)(v0 + dv - sgv) + 0.5f * (float)sgv);
+  const double du_ = __dmul_rn(2.0, fabs(__dsub_rn(uc, um)));
+  const double dv_ = __dmul_rn(2.0, fabs(__dsub_rn(vc, vm)));
+  const double omu = __dsub_rn(1.0, du_), omv = __dsub_rn(1.0, dv_);
+  const double sw[4] = {__dmul_rn(omu, omv), __dmul_rn(omv, du_), __dmul_rn(omu, dv_), __dmul_rn(du_, dv_)};
+  const int cu[4] = {du - sgu, du, du - sgu, du}, cv[4] = {dv - sgv, dv - sgv, dv, dv};
+  double cH[4], c0[4], c1[4];
+  for (int q = 0; q < 4; q++) {
+    int o[3];
+    if (ax == 2) { o[0] = cu[q]; o[1] = cv[q]; o[2] = dw - sgw; }
+    else if (ax == 1) { o[0] = cu[q]; o[2] = cv[q]; o[1] = dw - sgw; }
+    else { o[1] = cu[q]; o[2] = cv[q]; o[0] = dw - sgw; }
+    const size_t p = (size_t)wrap0(i0 + o[0], m0) + (size_t)m0 * ((size_t)wrap0(j0 + o[1], m1) + (size_t)m1 * wrap0(k0 + o[2], m2));
+    cH[q] = cdh[p]; c0[q] = cdhe[p]; c1[q] = cdhe[p + N3];
+  }
+  double r3[3];
+  const double* cc[3] = {cH, c0, c1};
+  const double sg[3] = {sigma_HI_at_ion_freq, sigma_HeI_at_ion_freq, sigma_HeII_at_ion_freq};
+  for (int s = 0; s < 3; s++) {
+    double num = 0.0, den = 0.0;
+    for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf(cc[s][q], sg[s]); num += cc[s][q] * w; den += w; }
+    r3[s] = num / den;
+  }
+  const int wa = abs(dw), ua = abs(du), va = abs(dv);
+  if (wa == 1 && (ua == 1 || va == 1)) {
+    const double f = (ua == 1 && va == 1) ? sqrt3 : sqrt2;
+    r3[0] *= f; r3[1] *= f; r3[2] *= f;
+  }
+  out4[4 * t] = r3[0]; out4[4 * t + 1] = r3[1]; out4[4 * t + 2] = r3[2];
+  out4[4 * t + 3] = sqrt((fu * fu + fv * fv) / (fw * fw) + 1.0);
+}
+
+// FP64 FMA throughput probe
+__global__ void k_fp64_probe(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace c2

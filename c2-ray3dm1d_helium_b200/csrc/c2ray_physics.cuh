@@ -1,0 +1,444 @@
+// c2ray_physics.cuh -- per-cell device physics of the C2-Ray H+He hot path (sm_100a, FP64).
+//
+// Written for registers, not as a translation: the reference's module globals (recombination /
+// collisional coefficients, cgsconstants.f90:105-133) become a per-thread struct, its 47-element per-cell
+// work arrays (radiation_photoionrates.f90:147-159) are never materialised -- photoion_rates streams over the
+// frequency bands keeping only accumulators -- and the secondary-ionisation factors are hoisted out of the
+// per-SED loop.  Each function cites the reference lines whose arithmetic it must reproduce.
+#pragma once
+#include "c2ray_consts.cuh"
+
+namespace c2 {
+
+// ------------------------------------------------------------------------------------------------
+// Device-visible tables and per-run constants
+// ------------------------------------------------------------------------------------------------
+struct SedDev {
+  const double* photo_thick;  // [band][0:NumTau]
+  const double* photo_thin;
+  const double* heat_thick;   // [heatbin][0:NumTau]
+  const double* heat_thin;
+  int lo, hi;                 // 1-based FreqBnd limits (hi < lo : SED absent)
+  double S_star;
+};
+
+struct BandConst {  // radiation_sizes.f90 arrays, 0-based band index
+  double sigma_HI[NumFreqBnd], sigma_HeI[NumFreqBnd], sigma_HeII[NumFreqBnd];
+  double f1ion_HI[NumFreqBnd], f1ion_HeI[NumFreqBnd], f1ion_HeII[NumFreqBnd];
+  double f2ion_HI[NumFreqBnd], f2ion_HeI[NumFreqBnd], f2ion_HeII[NumFreqBnd];
+  double f1heat_HI[NumFreqBnd], f1heat_HeI[NumFreqBnd], f1heat_HeII[NumFreqBnd];
+  double f2heat_HI[NumFreqBnd], f2heat_HeI[NumFreqBnd], f2heat_HeII[NumFreqBnd];
+};
+
+struct RunConst {
+  SedDev sed[3];
+  int isothermal, cosmological;
+  double temper_val;
+  double clumping;        // (double) of the reference's real
+  double cosmo_coef;      // 2.0/(1.0+zred)*dzdt  applied as e_int*2.0/(1.0+zred)*dzdt
+  double zp1, dzdt;
+  double dr[3], vol;
+  double cool_mintemp, cool_dtemp;
+  const double* cool;     // 5 x 801 linear cooling tables: h0,h1,he0,he1,he2
+  int mesh[3];
+};
+
+__constant__ BandConst d_band;
+__constant__ RunConst d_run;
+
+struct RecCol {
+  double arech0, brech0, areche0, breche0, oreche0, areche1, breche1, treche1;
+  double colli_HI, colli_HeI, colli_HeII, v;
+};
+
+struct Ion {
+  double h0, h1, he0, he1, he2;
+  double h_av0, h_av1, he_av0, he_av1, he_av2;
+  double h_old0, h_old1, he_old0, he_old1, he_old2;
+};
+
+// ------------------------------------------------------------------------------------------------
+// cgsconstants.f90:140-266 ini_rec_colion_factors (literal kinds reproduced, see FL())
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ini_rec_colion_factors(double T, RecCol& r) {
+  double lambda = 2.0 * (temph0 / T);
+  // the H fit is shared by arech0/brech0 and (T<9e3) areche0/breche0 up to the leading literal
+  const double hA = pow(lambda, 1.503) / pow(1.0 + pow(lambda / FL(0.522f), FL(0.470f)), FL(1.923f));
+  const double hB = pow(lambda, 1.500) / pow(1.0 + pow(lambda / FL(2.740f), FL(0.407f)), FL(2.242f));
+  r.arech0 = FL(1.269e-13f) * hA;
+  r.brech0 = FL(2.753e-14f) * hB;
+  if (T < 9.e3) {
+    r.areche0 = 1.269e-13 * hA;
+    r.breche0 = 2.753e-14 * hB;
+  } else {
+    const double lam0 = 2.0 * (temphe0 / T);
+    const double dielectronic = 1.9e-3 * pow(T, -1.5) * exp(-4.7e5 / T) * (1.0 + 0.3 * exp(-9.4e4 / T));
+    r.areche0 = 3.000e-14 * pow(lam0, 0.654) + dielectronic;
+    r.breche0 = 1.260e-14 * pow(lam0, 0.750) + dielectronic;
+  }
+  r.oreche0 = r.areche0 - r.breche0;
+  lambda = 2.0 * (temphe1 / T);
+  r.breche1 = 5.5060e-14 * pow(lambda, 1.5) / pow(1.0 + pow(lambda / 2.740, 0.407), 2.242);
+  r.areche1 = FL(2.538e-13f) * pow(lambda, 1.503) / pow(1.0 + pow(lambda / 0.522, 0.470), 1.923);
+  r.treche1 = 3.4e-13 * pow(T / 1.0e4, -0.6);
+  r.v = 0.285 * pow(T / 1.0e4, 0.119);
+  const double sqrtt0 = sqrt(T);
+  r.colli_HI = colh0 * sqrtt0 * exp(-temph0 / T);
+  r.colli_HeI = colhe0 * sqrtt0 * exp(-temphe0 / T);
+  r.colli_HeII = colhe1 * sqrtt0 * exp(-temphe1 / T);
+}
+
+// tped.f90:75-84
+__device__ __forceinline__ double electrondens(double n, double xh1, double xhe1, double xhe2) {
+  return n * (xh1 * (1.0 - abu_he) + abu_c + abu_he * (xhe1 + 2.0 * xhe2));
+}
+
+// cooling_h.f90:40-71
+__device__ __forceinline__ double coolin(double n, double ne, double h_av0, double h_av1, double he_av0, double he_av1,
+                                         double he_av2, double T, const double* __restrict__ ct) {
+  const double tpos = (log10(T) - d_run.cool_mintemp) / d_run.cool_dtemp + 1.0;
+  const int itpos = min(TEMPPOINTS - 1, max(1, (int)tpos));
+  const double dtpos = tpos - (double)itpos;
+  const int a = itpos - 1, b = min(TEMPPOINTS, itpos + 1) - 1;
+  const double c0 = ct[a] + (ct[b] - ct[a]) * dtpos;
+  const double c1 = ct[TEMPPOINTS + a] + (ct[TEMPPOINTS + b] - ct[TEMPPOINTS + a]) * dtpos;
+  const double c2v = ct[2 * TEMPPOINTS + a] + (ct[2 * TEMPPOINTS + b] - ct[2 * TEMPPOINTS + a]) * dtpos;
+  const double c3 = ct[3 * TEMPPOINTS + a] + (ct[3 * TEMPPOINTS + b] - ct[3 * TEMPPOINTS + a]) * dtpos;
+  const double c4 = ct[4 * TEMPPOINTS + a] + (ct[4 * TEMPPOINTS + b] - ct[4 * TEMPPOINTS + a]) * dtpos;
+  return n * ne * ((h_av0 * c0 + h_av1 * c1) * (1.0 - abu_he) + (he_av0 * c2v + he_av1 * c3 + he_av2 * c4) * abu_he);
+}
+
+// doric.f90:317-351 prepare_doric_factors with coldens (:358-372) at path = 1
+struct DoricFrac { double y, z, y2a, y2b; };
+__device__ __forceinline__ DoricFrac prepare_doric_factors(double n, double h0, double he0, double he1) {
+  const double NH = h0 * n * 1.0 * (1.0 - abu_he);
+  const double NHe0 = he0 * n * 1.0 * abu_he;
+  const double NHe1 = he1 * n * 1.0 * abu_he;
+  const double tau_H_heth = NH * sigma_H_heth, tau_He_heth = NHe0 * sigma_HeI_at_ion_freq;
+  const double tau_H_heLya = NH * sigma_H_heLya, tau_He_heLya = NHe0 * sigma_He_heLya;
+  const double tau_H_he2th = NH * sigma_H_he2, tau_He_he2th = NHe0 * sigma_He_he2;
+  const double tau_He2_he2th = NHe1 * sigma_HeII_at_ion_freq;
+  DoricFrac f;
+  f.y = tau_H_heth / (tau_H_heth + tau_He_heth);
+  f.z = tau_H_heLya / (tau_H_heLya + tau_He_heLya);
+  const double den = tau_He2_he2th + tau_He_he2th + tau_H_he2th;
+  f.y2a = tau_He2_he2th / den;
+  f.y2b = tau_He_he2th / den;
+  return f;
+}
+
+// doric.f90:35-313
+__device__ __forceinline__ void doric(double dt, double rhe, Ion& ion, double phiHI, double phiHeI, double phiHeII,
+                                      const DoricFrac& fr, const RecCol& rc, double clumping) {
+  const double pfrac = 0.96;
+  const double heliumfraction = abu_he / (1.0 - abu_he);
+  const double ffrac = fmax(fmin(10.0 * ion.h0, 1.0), 0.01);
+  const double wfrac = (1.425 - 0.737) + 0.737 * fr.y;
+  const double v = rc.v;
+  const double alpha_h_B = clumping * rc.brech0;
+  const double alpha_he_1 = clumping * rc.oreche0;
+  const double alpha_he_B = clumping * rc.breche0;
+  const double alpha_he_A = clumping * rc.areche0;
+  const double alpha_he2_B = clumping * rc.breche1;
+  const double alpha_he2_A = clumping * rc.areche1;
+  const double alpha_he2_2 = clumping * rc.treche1;
+  const double alpha_he2_1 = alpha_he2_A - alpha_he2_B;
+  const double aih0 = fmax(phiHI + rhe * rc.colli_HI, 1.0e-200);
+  const double aihe0 = fmax(phiHeI + rhe * rc.colli_HeI, 1.0e-200);
+  const double aihe1 = fmax(phiHeII + rhe * rc.colli_HeII, 1.0e-200);
+
+  const double Lmat = -(aih0 + rhe * alpha_h_B);
+  const double Mmat = (fr.y * rhe * alpha_he_1 + pfrac * rhe * alpha_he_B) * heliumfraction;
+  const double Nmat = ((ffrac * fr.z * (1.0 - v) + v * wfrac) * alpha_he2_B + alpha_he2_2 +
+                       (1.0 - fr.y2a - fr.y2b) * alpha_he2_1) * heliumfraction * rhe;
+  const double Pmat = -aihe0 - aihe1 - rhe * (alpha_he_A - (1.0 - fr.y) * alpha_he_1);
+  const double Emat = -rhe * (alpha_he2_A - fr.y2a * alpha_he2_1);
+  const double Qmat = -aihe0 + rhe * alpha_he2_B * (ffrac * (1.0 - fr.z) * (1.0 - v) + v * (1.425 - wfrac)) - Emat +
+                      alpha_he2_1 * fr.y2b * rhe;
+  const double Bcoef = Emat - Pmat;
+  const double Scoef = sqrt(Bcoef * Bcoef + 4.0 * aihe1 * Qmat);
+  const double QHEPcoef = 1.0 / (Qmat * aihe1 - Emat * Pmat);
+  const double BminusS = Bcoef - Scoef, BplusS = Bcoef + Scoef;
+  const double lambda1 = Lmat;
+  const double lambda2 = 0.5 * (Emat + Pmat - Scoef);
+  const double lambda3 = 0.5 * (Emat + Pmat + Scoef);
+  const double rx = -1.0 / Lmat * (aih0 + (Mmat * Emat - Nmat * aihe1) * (aihe0 * QHEPcoef));
+  const double ry = aihe0 * (Emat * QHEPcoef);
+  const double rz = -aihe0 * (aihe1 * QHEPcoef);
+  const double twoaihe1 = 2.0 * aihe1;
+  const double eigv2x = -Nmat / (Lmat - lambda2) + (Mmat / twoaihe1) * BplusS / (Lmat - lambda2);
+  const double eigv3x = (-twoaihe1 * Nmat + Mmat * BminusS) / (twoaihe1 * (Lmat - lambda3));
+  const double eigv2y = (-BplusS) / twoaihe1;
+  const double eigv3y = (-BminusS) / twoaihe1;
+  const double Rcoef = twoaihe1 * (ry - ion.he_old1);
+  const double Tcoef = rz - ion.he_old2;
+  const double twoS = 2.0 * Scoef;
+  const double coef2 = (Rcoef + BminusS * Tcoef) / twoS;
+  const double coef3 = -(Rcoef + BplusS * Tcoef) / twoS;
+  const double coef1 = -rx + (eigv3x - eigv2x) * (Rcoef / twoS) +
+                       Tcoef * (BplusS * eigv3x / twoS - BminusS * eigv2x / twoS) + ion.h_old1;
+  const double lam1dt = dt * lambda1, lam2dt = dt * lambda2, lam3dt = dt * lambda3;
+  const double elam1dt = exp(lam1dt), elam2dt = exp(lam2dt), elam3dt = exp(lam3dt);
+
+  ion.h1 = coef1 * elam1dt + coef2 * elam2dt * eigv2x + coef3 * elam3dt * eigv3x + rx;
+  ion.he1 = coef2 * elam2dt * eigv2y + coef3 * elam3dt * eigv3y + ry;
+  ion.he2 = coef2 * elam2dt + coef3 * elam3dt + rz;
+  ion.h0 = 1.0 - ion.h1;
+  ion.he0 = 1.0 - ion.he1 - ion.he2;
+  if (ion.h0 < epsilon) { ion.h0 = epsilon; ion.h1 = 1.0 - epsilon; }
+  if (ion.h1 < epsilon) { ion.h1 = epsilon; ion.h0 = 1.0 - epsilon; }
+  if ((ion.he0 <= epsilon) || (ion.he1 <= epsilon) || (ion.he2 <= epsilon)) {
+    if (ion.he0 < epsilon) ion.he0 = epsilon;
+    if (ion.he1 < epsilon) ion.he1 = epsilon;
+    if (ion.he2 < epsilon) ion.he2 = epsilon;
+    const double normfac = ion.he0 + ion.he1 + ion.he2;
+    ion.he0 = ion.he0 / normfac; ion.he1 = ion.he1 / normfac; ion.he2 = ion.he2 / normfac;
+  }
+  const double lim = FL(1.0e-8f);
+  const double af1 = (fabs(lam1dt) < lim) ? coef1 : coef1 * (elam1dt - 1.0) / lam1dt;
+  const double af2 = (fabs(lam2dt) < lim) ? coef2 : coef2 * (elam2dt - 1.0) / lam2dt;
+  const double af3 = (fabs(lam3dt) < lim) ? coef3 : coef3 * (elam3dt - 1.0) / lam3dt;
+  ion.h_av1 = rx + af1 + eigv2x * af2 + eigv3x * af3;
+  ion.he_av1 = ry + eigv2y * af2 + eigv3y * af3;
+  ion.he_av2 = rz + af2 + af3;
+  ion.h_av0 = 1.0 - ion.h_av1;
+  ion.he_av0 = 1.0 - ion.he_av1 - ion.he_av2;
+  if (ion.h_av1 < epsilon) { ion.h_av1 = epsilon; ion.h_av0 = 1.0 - epsilon; }
+  if (ion.h_av0 < epsilon) { ion.h_av0 = epsilon; ion.h_av1 = 1.0 - epsilon; }
+  if ((ion.he_av0 <= epsilon) || (ion.he_av1 <= epsilon) || (ion.he_av2 <= epsilon)) {
+    if (ion.he_av1 < epsilon) ion.he_av1 = epsilon;
+    if (ion.he_av2 < epsilon) ion.he_av2 = epsilon;
+    if (ion.he_av0 < epsilon) ion.he_av0 = epsilon;
+    const double normfac = ion.he_av0 + ion.he_av1 + ion.he_av2;
+    ion.he_av0 = ion.he_av0 / normfac; ion.he_av1 = ion.he_av1 / normfac; ion.he_av2 = ion.he_av2 / normfac;
+  }
+}
+
+// thermal.f90:22-174 ; returns the number of sub-steps
+__device__ __forceinline__ int thermal(double dt, double& end_temper, double& avg_temper, double ne, double n,
+                                       const Ion& ion, double heating) {
+  double internal_energy = (n + electrondens(n, ion.h_old1, ion.he_old1, ion.he_old2)) * k_B * end_temper / gamma1;
+  const double cosmo_cool_rate =
+      d_run.cosmological ? internal_energy * FL(2.0f) / d_run.zp1 * d_run.dzdt : 0.0;  // cosmology.f90:232
+  int i_heating = 0;
+  if (end_temper > minitemp) {
+    const double* __restrict__ ct = d_run.cool;
+    const double ne_av = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
+    const double kn_av = k_B * (n + ne_av);
+    double cumulative_time = 0.0;
+    avg_temper = 0.0;
+    const double initial_temp = end_temper;
+    const double tol = FL(1e-6f) * dt;
+    for (;;) {
+      i_heating++;
+      const double cooling =
+          coolin(n, ne, ion.h_av0, ion.h_av1, ion.he_av0, ion.he_av1, ion.he_av2, end_temper, ct) + cosmo_cool_rate;
+      const double thermal_rate = fmax(1e-50, fabs(cooling - heating));
+      const double thermal_timescale = internal_energy / fabs(thermal_rate);
+      const double dt_thermal = relative_denergy * thermal_timescale;
+      const double dt_ODE = fmin(dt_thermal, dt - cumulative_time);
+      internal_energy = internal_energy + dt_ODE * (heating - cooling);
+      avg_temper = avg_temper + FL(0.5f) * end_temper * dt_ODE;
+      end_temper = (internal_energy * gamma1) / kn_av;
+      avg_temper = avg_temper + FL(0.5f) * end_temper * dt_ODE;
+      if (end_temper < minitemp) {
+        internal_energy = (n + ne_av) * k_B * minitemp;  // thermal.f90:141 (no /gamma1, as in the reference)
+        end_temper = minitemp;
+      }
+      cumulative_time = cumulative_time + dt_ODE;
+      if (cumulative_time >= dt || fabs(cumulative_time - dt) < tol) break;
+      if (i_heating > 10000) break;
+    }
+    avg_temper = (dt > 0.0) ? avg_temper / dt : initial_temp;
+    end_temper = (internal_energy * gamma1) / (k_B * (n + electrondens(n, ion.h1, ion.he1, ion.he2)));
+  }
+  return i_heating;
+}
+
+// evolve_point.F90:444-646 do_chemistry (local=.false.); temper1 in: T_old (grid(..,2)); avg_temper in: grid(..,1)
+__device__ __forceinline__ int do_chemistry(double dt, double n, Ion& ion, double phiHI, double phiHeI, double phiHeII,
+                                            double heat, double temper_old, double& avg_temper, double& temper1_out,
+                                            RecCol& rc) {
+  const bool iso = d_run.isothermal != 0;
+  const double clumping = d_run.clumping;
+  double temper1 = temper_old;
+  const double temper0 = temper1;
+  int nit = 0;
+  for (;;) {
+    nit++;
+    const double temper2 = temper1;
+    const double yh0_av_old = ion.h_av0, yhe0_av_old = ion.he_av0, yhe2_av_old = ion.he_av2;
+    double de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
+    if (!iso) ini_rec_colion_factors(avg_temper, rc);
+    DoricFrac fr = prepare_doric_factors(n, ion.h0, ion.he0, ion.he1);
+    doric(dt, de, ion, phiHI, phiHeI, phiHeII, fr, rc, clumping);
+    de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
+    fr = prepare_doric_factors(n, ion.h0, ion.he0, ion.he1);
+    const double ionh0old = ion.h0, ionh1old = ion.h1, ionhe0old = ion.he0, ionhe1old = ion.he1, ionhe2old = ion.he2;
+    const double oldhav = ion.h_av0, oldhe0av = ion.he_av0, oldhe1av = ion.he_av1;
+    doric(dt, de, ion, phiHI, phiHeI, phiHeII, fr, rc, clumping);
+    // evolve_point.F90:588-595: h_av(1) and he_av(2) keep their pass-2 values
+    ion.h0 = (ion.h0 + ionh0old) / 2.0;
+    ion.h1 = (ion.h1 + ionh1old) / 2.0;
+    ion.he0 = (ion.he0 + ionhe0old) / 2.0;
+    ion.he1 = (ion.he1 + ionhe1old) / 2.0;
+    ion.he2 = (ion.he2 + ionhe2old) / 2.0;
+    ion.h_av0 = (ion.h_av0 + oldhav) / 2.0;
+    ion.he_av0 = (ion.he_av0 + oldhe0av) / 2.0;
+    ion.he_av1 = (ion.he_av1 + oldhe1av) / 2.0;
+    de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
+    temper1 = temper0;
+    if (!iso) thermal(dt, temper1, avg_temper, de, n, ion, heat);
+    const bool ok =
+        (fabs((ion.h_av0 - yh0_av_old) / ion.h_av0) < minimum_fractional_change || ion.h_av0 < minimum_fraction_of_atoms) &&
+        (fabs((ion.he_av0 - yhe0_av_old) / ion.he_av0) < minimum_fractional_change || ion.he_av0 < minimum_fraction_of_atoms) &&
+        (fabs((ion.he_av2 - yhe2_av_old) / ion.he_av2) < minimum_fractional_change || ion.he_av2 < minimum_fraction_of_atoms) &&
+        (fabs((temper1 - temper2) / temper1) < minimum_fractional_change);
+    if (ok) break;
+    if (nit > 400) break;
+  }
+  temper1_out = temper1;
+  return nit;
+}
+
+// ------------------------------------------------------------------------------------------------
+// radiation_photoionrates.f90:108-277 photoion_rates, streamed over the frequency bands.
+// ------------------------------------------------------------------------------------------------
+struct TauPos { int ipos, ipos_p1; double residual; };
+
+__device__ __forceinline__ TauPos tau_table_position(double tau) {  // :282-306
+  const double lt = log10(fmax(1.0e-20, tau));
+  const double odpos = fmin((double)NumTau, fmax(0.0, 1.0 + (lt - minlogtau) / dlogtau));
+  TauPos p;
+  p.ipos = (int)odpos;
+  p.residual = odpos - (double)p.ipos;
+  p.ipos_p1 = min(NumTau, p.ipos + 1);
+  return p;
+}
+__device__ __forceinline__ double read_table(const double* __restrict__ col, const TauPos& p) {  // :310-326
+  const double a = __ldg(col + p.ipos), b = __ldg(col + p.ipos_p1);
+  return a + (b - a) * p.residual;
+}
+
+struct PhotOut { double photo_HI, photo_HeI, photo_HeII, heat, photo_in, photo_out; };
+
+__device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, double in_HeI, double out_HeI,
+                                                  double in_HeII, double out_HeII, double vol, const double nflux[3],
+                                                  double i_state) {
+  PhotOut r = {0, 0, 0, 0, 0, 0};
+  const double cell_HI = out_HI - in_HI, cell_HeI = out_HeI - in_HeI, cell_HeII = out_HeII - in_HeII;
+  const bool iso = d_run.isothermal != 0;
+  bool act[3];
+  int blo = NumFreqBnd + 1, bhi = 0;
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    act[s] = (d_run.sed[s].hi >= d_run.sed[s].lo) && (nflux[s] > 0.0);
+    if (act[s]) { blo = min(blo, d_run.sed[s].lo); bhi = max(bhi, d_run.sed[s].hi); }
+  }
+  // secondary ionisation (Ricotti et al. 2002), :557-565 -- depends on the cell only
+  double y1R0 = 0, y1R1 = 0, y1R2 = 0, y2R0 = 0, y2R1 = 0, y2R2 = 0;
+  if (!iso) {
+    y1R0 = 0.3908 * pow(1.0 - pow(i_state, 0.4092), 1.7592);
+    y1R1 = 0.0554 * pow(1.0 - pow(i_state, 0.4614), 1.6660);
+    y1R2 = 1.0 * pow(1.0 - pow(i_state, 0.2663), 1.3163);
+    const double xeb01 = 1.0 - pow(i_state, 0.38);  // bR2(1) == bR2(2)
+    const double xeb2 = 1.0 - pow(i_state, 0.34);
+    const double p02 = pow(i_state, 0.2);            // aR2(1) == aR2(2)
+    y2R0 = 0.6941 * p02 * xeb01 * xeb01;
+    y2R1 = 0.0984 * p02 * xeb01 * xeb01;
+    y2R2 = 3.9811 * pow(i_state, 0.4) * xeb2 * xeb2;
+  }
+  double f_heat = 0.0, f_ion_HI = 0.0, f_ion_HeI = 0.0;
+
+  for (int b = blo; b <= bhi; b++) {  // 1-based band
+    const int q = b - 1;
+    const double sHI = d_band.sigma_HI[q], sHeI = d_band.sigma_HeI[q], sHeII = d_band.sigma_HeII[q];
+    const double tau_in = in_HI * sHI + in_HeI * sHeI + in_HeII * sHeII;     // :172-176
+    const double tau_out = out_HI * sHI + out_HeI * sHeI + out_HeII * sHeII;  // :179-183
+    const TauPos pin = tau_table_position(tau_in);
+    const double dtau = tau_out - tau_in;
+    const bool thick_p = fabs(dtau) > tau_photo_limit;
+    const bool thick_h = fabs(dtau) > tau_heat_limit;
+    TauPos pout;
+    if (thick_p) pout = tau_table_position(tau_out); else { pout.ipos = 0; pout.ipos_p1 = 0; pout.residual = 0; }
+    // species scalings :787-825 and per-species cell optical depths :236-240
+    const double tcHI = cell_HI * sHI, tcHeI = cell_HeI * sHeI, tcHeII = cell_HeII * sHeII;
+    double scHI = 1.0, scHeI = 0.0, scHeII = 0.0;
+    int hcol = 0, nsp = 1;
+    if (b > NumBndin1 + NumBndin2) {
+      const double f = 1.0 / (sHI * cell_HI + sHeI * cell_HeI + sHeII * cell_HeII);
+      scHI = tcHI * f; scHeI = tcHeI * f; scHeII = tcHeII * f;
+      hcol = 3 * b - NumBndin2 - NumBndin1 * 2 - 2 - 1; nsp = 3;
+    } else if (b > NumBndin1) {
+      const double f = 1.0 / (sHI * cell_HI + sHeI * cell_HeI);
+      scHI = sHI * cell_HI * f; scHeI = sHeI * cell_HeI * f;
+      hcol = 2 * b - NumBndin1 - 1 - 1; nsp = 2;
+    }
+    double ph_HI = 0.0, ph_HeI = 0.0, ph_HeII = 0.0;  // this band's heating per species, all SEDs
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      if (!act[s] || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
+      const SedDev& T = d_run.sed[s];
+      const double NFlux = nflux[s];
+      const size_t off = (size_t)q * (NumTau + 1);
+      // photo_lookuptable :390-460
+      const double phi_in = NFlux * read_table(T.photo_thick + off, pin);
+      double phi_all, phi_out;
+      if (thick_p) {
+        phi_out = NFlux * read_table(T.photo_thick + off, pout);
+        phi_all = phi_in - phi_out;
+      } else {
+        phi_all = NFlux * dtau * read_table(T.photo_thin + off, pin);
+        phi_out = phi_in - phi_all;
+      }
+      r.photo_in += phi_in;
+      r.photo_out += phi_out;
+      r.photo_HI += scHI * phi_all / vol;
+      if (nsp >= 2) r.photo_HeI += scHeI * phi_all / vol;
+      if (nsp == 3) r.photo_HeII += scHeII * phi_all / vol;
+      // heat_lookuptable :586-760
+      if (!iso) {
+        const size_t ho = (size_t)hcol * (NumTau + 1);
+        if (thick_h) {
+          ph_HI += scHI * (NFlux * read_table(T.heat_thick + ho, pin) - NFlux * read_table(T.heat_thick + ho, pout)) / vol;
+          if (nsp >= 2)
+            ph_HeI += scHeI * (NFlux * read_table(T.heat_thick + ho + (NumTau + 1), pin) -
+                               NFlux * read_table(T.heat_thick + ho + (NumTau + 1), pout)) / vol;
+          if (nsp == 3)
+            ph_HeII += scHeII * (NFlux * read_table(T.heat_thick + ho + 2 * (NumTau + 1), pin) -
+                                 NFlux * read_table(T.heat_thick + ho + 2 * (NumTau + 1), pout)) / vol;
+        } else {
+          ph_HI += NFlux * tcHI * read_table(T.heat_thin + ho, pin) / vol;
+          if (nsp >= 2) ph_HeI += NFlux * tcHeI * read_table(T.heat_thin + ho + (NumTau + 1), pin) / vol;
+          if (nsp == 3) ph_HeII += NFlux * tcHeII * read_table(T.heat_thin + ho + 2 * (NumTau + 1), pin) / vol;
+        }
+      }
+    }
+    if (!iso) {
+      // the secondary-ionisation bookkeeping is linear in the per-species heating, so the SED sum can be
+      // taken first (:654-669, :739-759)
+      double df_heat = ph_HI + ph_HeI + ph_HeII;
+      if (b > NumBndin1) {
+        const double fs1 = d_band.f1ion_HI[q] * ph_HI + d_band.f1ion_HeI[q] * ph_HeI + d_band.f1ion_HeII[q] * ph_HeII;
+        const double fs2 = d_band.f2ion_HI[q] * ph_HI + d_band.f2ion_HeI[q] * ph_HeI + d_band.f2ion_HeII[q] * ph_HeII;
+        const double fs3 = d_band.f1heat_HI[q] * ph_HI + d_band.f1heat_HeI[q] * ph_HeI + d_band.f1heat_HeII[q] * ph_HeII;
+        const double fs4 = d_band.f2heat_HI[q] * ph_HI + d_band.f2heat_HeI[q] * ph_HeI + d_band.f2heat_HeII[q] * ph_HeII;
+        f_ion_HeI += y1R1 * fs1 - y2R1 * fs2;
+        f_ion_HI += y1R0 * fs1 - y2R0 * fs2;
+        df_heat = df_heat - y1R2 * fs3 + y2R2 * fs4;
+      }
+      f_heat += df_heat;
+    }
+  }
+  if (!iso) {
+    r.heat = f_heat;
+    r.photo_HI += f_ion_HI / (ion_freq_HI * hplanck);
+    r.photo_HeI += f_ion_HeI / (ion_freq_HeI * hplanck);
+  }
+  return r;
+}
+
+// column_density.f90:351-376
+__device__ __forceinline__ double weightf(double cd, double sig) { return 1.0 / fmax(0.6, cd * sig); }
+
+}  // namespace c2
