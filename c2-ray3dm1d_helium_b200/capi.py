@@ -21,6 +21,7 @@ EXPORTS = [
     "c2ray_b200_chemistry_batch", "c2ray_b200_rec_colion_batch", "c2ray_b200_cinterp_batch",
     "c2ray_b200_comm_unique_id", "c2ray_b200_comm_init", "c2ray_b200_set_rank", "c2ray_b200_rates_device_buffer",
     "c2ray_b200_bench_global_pass", "c2ray_b200_launch_count", "c2ray_b200_measure_fp64", "c2ray_b200_stream",
+    "c2ray_b200_timer_start", "c2ray_b200_timer_stop",
 ]
 
 

@@ -114,6 +114,7 @@ struct c2ray_ctx {
   int64_t launches = 0;
   bool run_dirty = true;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_timer[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -377,6 +378,7 @@ int c2ray_b200_init(const c2ray_params* params, const int32_t mesh[3], int32_t d
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
+  for (auto& ev : c->ev_timer) CK(cudaEventCreate(&ev));
   c->rates_count = 4 * N3 + NumFreqBnd + 1;
   CK(cudaMalloc(&c->ndens, N3 * 8));
   CK(cudaMalloc(&c->xh, 2 * N3 * 8)); CK(cudaMalloc(&c->xhe, 3 * N3 * 8));
@@ -409,6 +411,7 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ev_timer) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->stream);
   if (g_bound == c) g_bound = nullptr;
   delete c;
@@ -977,6 +980,24 @@ int c2ray_b200_measure_fp64(c2ray_ctx* c, double* tflops) {
   }
   cudaFree(d);
   *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+  return C2RAY_OK;
+}
+
+int c2ray_b200_timer_start(c2ray_ctx* c) {
+  if (!c) return fail(C2RAY_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaEventRecord(c->ev_timer[0], c->stream));
+  return C2RAY_OK;
+}
+int c2ray_b200_timer_stop(c2ray_ctx* c, double* ms) {
+  if (!c || !ms) return fail(C2RAY_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(c->ev_timer[1], c->stream));
+  CK(cudaEventSynchronize(c->ev_timer[1]));
+  float f;
+  CK(cudaEventElapsedTime(&f, c->ev_timer[0], c->ev_timer[1]));
+  *ms = f;
   return C2RAY_OK;
 }
 

@@ -293,6 +293,14 @@ class C2Ray:
         capi.check(self.lib.c2ray_b200_bench_global_pass(self.ctx, C.c_double(dt), C.c_int32(reps), C.byref(ms), C.byref(cf)))
         return ms.value, cf.value
 
+    def timer_start(self):
+        capi.check(self.lib.c2ray_b200_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        capi.check(self.lib.c2ray_b200_timer_stop(self.ctx, C.byref(ms)))
+        return ms.value
+
     def launch_count(self):
         return int(self.lib.c2ray_b200_launch_count(self.ctx))
 

@@ -43,7 +43,7 @@ def lognormal_field(n, sigma, seed, smooth_cells=2.0):
     k = np.fft.fftfreq(n) * 2 * np.pi
     kz, ky, kx = np.meshgrid(k, k, np.fft.rfftfreq(n) * 2 * np.pi, indexing="ij")
     filt = np.exp(-0.5 * (kx * kx + ky * ky + kz * kz) * smooth_cells ** 2)
-    g = np.fft.irfftn(np.fft.rfftn(g) * filt, s=(n, n, n))
+    g = np.fft.irfftn(np.fft.rfftn(g) * filt, s=(n, n, n), axes=(0, 1, 2))
     g *= sigma / g.std()
     rho = np.exp(g - 0.5 * sigma * sigma)
     return rho / rho.mean()

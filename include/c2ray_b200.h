@@ -187,6 +187,9 @@ int c2ray_b200_bench_global_pass(c2ray_ctx* ctx, double dt, int32_t reps, double
 int64_t c2ray_b200_launch_count(c2ray_ctx* ctx);
 /* FP64 FMA throughput microbenchmark (TFLOP/s), for the FP64 roofline denominator */
 int c2ray_b200_measure_fp64(c2ray_ctx* ctx, double* tflops);
+/* CUDA-event stopwatch on the context's stream (device time of everything enqueued between the two calls) */
+int c2ray_b200_timer_start(c2ray_ctx* ctx);
+int c2ray_b200_timer_stop(c2ray_ctx* ctx, double* ms);
 /* CUDA stream handle (cudaStream_t) the context launches on */
 int c2ray_b200_stream(c2ray_ctx* ctx, void** stream);
 

@@ -10,7 +10,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "libc2ray_oracle.so")
+LIB = os.path.join(HERE, os.environ.get("C2RAY_ORACLE_LIB", "libc2ray_oracle.so"))
 
 NUMTAU, NUMFREQBND, NUMHEATBIN = 2000, 47, 113
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -20,7 +20,8 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build(force=False):
     src = os.path.join(HERE, "c2ray_oracle.cpp")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src) or \
+            not os.path.exists(os.path.join(HERE, "libc2ray_oracle_fma.so")):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return LIB
 

@@ -49,3 +49,17 @@ def partially_ionized_state(p, seed=1):
     b = 10.0 ** rng.uniform(-8, 0, shape) * 0.39
     xhe = np.stack([1.0 - a - b, a, b])
     return xh, xhe
+
+
+# Ionization fractions: 1e-8 relative (BASELINE north_star) plus an absolute floor.  doric's closed-form solution
+# (doric.f90:222-224, :285-287) forms small fractions as differences of O(1) terms, so a fraction x carries an absolute
+# rounding noise of order 1e-11..1e-10 whatever its size: the CPU oracle compiled with and without FMA contraction
+# differs from itself by up to 8.6e-11 (tests/test_oracle_cpu.py::test_arithmetic_noise_floor measures this).
+FRAC_RTOL, FRAC_ATOL = 1e-8, 2e-10
+
+
+def frac_err(a, b):
+    """max |a-b| / (FRAC_RTOL*|b| + FRAC_ATOL) ; parity holds when < 1"""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / (FRAC_RTOL * np.abs(b) + FRAC_ATOL)))
