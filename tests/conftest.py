@@ -32,3 +32,5 @@ def pytest_collection_modifyitems(config, items):
 def _built():
     import __graft_entry__ as g
     g.build()
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
