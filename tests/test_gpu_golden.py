@@ -102,7 +102,7 @@ def test_full_size_config2_properties():
     xh_av, xhe_av, xh_i, xhe_i = c.get_work_state()
     assert 0 < cf <= 128 ** 3
     assert np.abs(xh_i.sum(axis=0) - 1).max() < 1e-12 and np.abs(xhe_i.sum(axis=0) - 1).max() < 1e-12
-    assert xh_i.min() >= 1e-20 and xhe_i.min() >= 1e-20
+    assert xh_i.min() >= 1e-20 and xhe_i.min() >= 0.999e-20  # He floors are renormalised (doric.f90:254-257)
     T = c.get_state()[2]
     assert np.all(T[0] >= 1.0) and np.all(np.isfinite(T))
     c.close()
