@@ -106,6 +106,7 @@ struct c2ray_ctx {
   SweepGeom geom{};
   ChemTotals* d_chem = nullptr;
   double* d_sums = nullptr;
+  double* d_secion = nullptr;
   int* d_nit = nullptr;
   // multi-GPU
   int rank = 0, npr = 1;
@@ -274,7 +275,11 @@ int sweep_all(c2ray_ctx* c) {
     const SweepGeom g = c->geom;
     int rmax = 0;
     for (int d = 0; d < 3; d++) rmax = std::max(rmax, std::max(g.R[d], g.L[d]));
-    GridPtrs G{c->ndens, c->xh_av, c->xhe_av, c->rates, c->N3};
+    if (!c->par.isothermal) {
+      if (!c->d_secion) CK(cudaMalloc(&c->d_secion, 6 * c->N3 * sizeof(double)));
+      LAUNCH(c, k_secion_factors, (unsigned)((c->N3 + 255) / 256), 256, c->xh_av, c->N3, c->d_secion);
+    }
+    GridPtrs G{c->ndens, c->xh_av, c->xhe_av, c->rates, c->d_secion, c->N3};
     const int batch = c->par.deterministic ? 1 : c->slots_cap;
     const int max_blocks = 148 * 16;
     for (int first = 0; first < c->n_mine; first += batch) {
@@ -289,7 +294,8 @@ int sweep_all(c2ray_ctx* c) {
         for (int r = r_lo; r <= r_hi; r++) {
           const long long items = (long long)ns * (r == 0 ? 1 : 24LL * r * r + 2);
           const int blocks = (int)std::min<long long>((items + 127) / 128, max_blocks);
-          LAUNCH(c, k_sweep_shell, blocks, 128, c->d_slots, c->d_active, c->d_tot, g, G, c->d_scratch, r);
+          if (c->par.isothermal) LAUNCH(c, k_sweep_shell<true>, blocks, 128, c->d_slots, c->d_active, c->d_tot, g, G, c->d_scratch, r);
+          else LAUNCH(c, k_sweep_shell<false>, blocks, 128, c->d_slots, c->d_active, c->d_tot, g, G, c->d_scratch, r);
         }
         if ((long long)g.subboxsize * b >= reach3) break;  // the do-while's extent test fails for every source
       }
@@ -407,7 +413,7 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   void* ptrs[] = {c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->rates, c->temp, c->snap_xh,
                   c->snap_xhe, c->snap_temp, c->d_srcpos, c->d_nf, c->d_nfpl, c->d_nfqpl, c->d_srcids, c->d_tb, c->d_cool,
-                  c->d_slots, c->d_active, c->d_tot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit};
+                  c->d_slots, c->d_active, c->d_tot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);

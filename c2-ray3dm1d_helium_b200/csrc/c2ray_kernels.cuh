@@ -8,7 +8,7 @@
 //   tables  k_build_tables: radiation_tables.f90 spec_integration on the device.
 #pragma once
 #include <cuda_runtime.h>
-#include "c2ray_physics.cuh"
+#include "c2ray_photo.cuh"
 
 namespace c2 {
 
@@ -135,10 +135,21 @@ struct GridPtrs {
   const double* xh_av;    // (N3,0:1)
   const double* xhe_av;   // (N3,0:2)
   double* rates;          // phih | phihe0 | phihe1 | phiheat, N3 each
+  const double* secion;   // (N3,6) secondary-ionisation factors y1R(1:3), y2R(1:3) of every cell (non-isothermal)
   size_t N3;
 };
 
+// radiation_photoionrates.f90:557-565 for every cell: depends on xh_av(1) only, so once per iteration, not per source
+__global__ void k_secion_factors(const double* __restrict__ xh_av, size_t N3, double* __restrict__ out) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N3) return;
+  const SecIon y = secion_factors(fmax(xh_av[p + N3], epsilon));  // i_state = ion%h_av(1), evolve_point.F90:123,257
+  out[p] = y.y1R0; out[p + N3] = y.y1R1; out[p + 2 * N3] = y.y1R2;
+  out[p + 3 * N3] = y.y2R0; out[p + 4 * N3] = y.y2R1; out[p + 5 * N3] = y.y2R2;
+}
+
 // One shell radius r of every active source.  Work item = (active slot, cell of the shell).
+template <bool ISO>
 __global__ void __launch_bounds__(128)
 k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot, SweepGeom g,
               GridPtrs G, double* __restrict__ scratch, int r) {
@@ -147,7 +158,7 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
   const long long total = (long long)nact * ncell;
   const size_t slot_stride = (size_t)6 * g.cap;                 // [parity][species][cap]
   const int par = r & 1;
-  const bool iso = d_run.isothermal != 0;
+  constexpr bool iso = ISO;
   const int m0 = d_run.mesh[0], m1 = d_run.mesh[1], m2 = d_run.mesh[2];
   unsigned int done = 0;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -166,7 +177,11 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     const size_t p = (size_t)wrap0(i0 + di, m0) + (size_t)m0 * ((size_t)wrap0(j0 + dj, m1) + (size_t)m1 * wrap0(k0 + dk, m2));
     const double ndens_p = G.ndens[p];
     const double h_av0 = fmax(G.xh_av[p], epsilon);
-    const double h_av1 = iso ? 0.0 : fmax(G.xh_av[p + G.N3], epsilon);
+    SecIon yR = {0, 0, 0, 0, 0, 0};
+    if (!iso) {
+      yR.y1R0 = G.secion[p]; yR.y1R1 = G.secion[p + G.N3]; yR.y1R2 = G.secion[p + 2 * G.N3];
+      yR.y2R0 = G.secion[p + 3 * G.N3]; yR.y2R1 = G.secion[p + 4 * G.N3]; yR.y2R2 = G.secion[p + 5 * G.N3];
+    }
     const double he_av0 = fmax(G.xhe_av[p], epsilon);
     const double he_av1 = fmax(G.xhe_av[p + G.N3], epsilon);
 
@@ -236,15 +251,15 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
       double num, den;
       num = 0.0; den = 0.0;
 #pragma unroll
-      for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf(cH[q], sigma_HI_at_ion_freq); num += cH[q] * w; den += w; }
+      for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf_fast(cH[q], sigma_HI_at_ion_freq); num += cH[q] * w; den += w; }
       cin_H = num / den;
       num = 0.0; den = 0.0;
 #pragma unroll
-      for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf(cHe0[q], sigma_HeI_at_ion_freq); num += cHe0[q] * w; den += w; }
+      for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf_fast(cHe0[q], sigma_HeI_at_ion_freq); num += cHe0[q] * w; den += w; }
       cin_He0 = num / den;
       num = 0.0; den = 0.0;
 #pragma unroll
-      for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf(cHe1[q], sigma_HeII_at_ion_freq); num += cHe1[q] * w; den += w; }
+      for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf_fast(cHe1[q], sigma_HeII_at_ion_freq); num += cHe1[q] * w; den += w; }
       cin_He1 = num / den;
       const int wa = abs(dw), ua = abs(du), va = abs(dv);
       if (wa == 1 && (ua == 1 || va == 1)) {  // :174-184
@@ -265,7 +280,7 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
 
     PhotOut phi = {0, 0, 0, 0, 0, 0};
     if (cin_H < max_coldensh) {  // :250-270
-      phi = photoion_rates(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, vol_ph, S.nflux, h_av1);
+      phi = photoion_rates<ISO>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, vol_ph, S.nflux, yR);
       phi.photo_HI = phi.photo_HI / (h_av0 * ndens_p * (1.0 - abu_he));
       phi.photo_HeI = phi.photo_HeI / (he_av0 * ndens_p * abu_he);
       phi.photo_HeII = phi.photo_HeII / (he_av1 * ndens_p * abu_he);
@@ -402,7 +417,9 @@ __global__ void k_photoion_batch(int n, const double* __restrict__ col6, const d
   if (t >= n) return;
   const double* q = col6 + 6 * (size_t)t;
   const double nflux[3] = {nf0, nf1, nf2};
-  const PhotOut r = photoion_rates(q[0], q[1], q[2], q[3], q[4], q[5], vol[t], nflux, i_state[t]);
+  const SecIon y = secion_factors(i_state[t]);
+  const PhotOut r = d_run.isothermal ? photoion_rates<true>(q[0], q[1], q[2], q[3], q[4], q[5], vol[t], nflux, y)
+                                     : photoion_rates<false>(q[0], q[1], q[2], q[3], q[4], q[5], vol[t], nflux, y);
   double* o = out6 + 6 * (size_t)t;
   o[0] = r.photo_HI; o[1] = r.photo_HeI; o[2] = r.photo_HeII; o[3] = r.heat; o[4] = r.photo_in; o[5] = r.photo_out;
 }

@@ -301,143 +301,6 @@ __device__ __forceinline__ int do_chemistry(double dt, double n, Ion& ion, doubl
   return nit;
 }
 
-// ------------------------------------------------------------------------------------------------
-// radiation_photoionrates.f90:108-277 photoion_rates, streamed over the frequency bands.
-// ------------------------------------------------------------------------------------------------
-struct TauPos { int ipos, ipos_p1; double residual; };
-
-__device__ __forceinline__ TauPos tau_table_position(double tau) {  // :282-306
-  const double lt = log10(fmax(1.0e-20, tau));
-  const double odpos = fmin((double)NumTau, fmax(0.0, 1.0 + (lt - minlogtau) / dlogtau));
-  TauPos p;
-  p.ipos = (int)odpos;
-  p.residual = odpos - (double)p.ipos;
-  p.ipos_p1 = min(NumTau, p.ipos + 1);
-  return p;
-}
-__device__ __forceinline__ double read_table(const double* __restrict__ col, const TauPos& p) {  // :310-326
-  const double a = __ldg(col + p.ipos), b = __ldg(col + p.ipos_p1);
-  return a + (b - a) * p.residual;
-}
-
-struct PhotOut { double photo_HI, photo_HeI, photo_HeII, heat, photo_in, photo_out; };
-
-__device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, double in_HeI, double out_HeI,
-                                                  double in_HeII, double out_HeII, double vol, const double nflux[3],
-                                                  double i_state) {
-  PhotOut r = {0, 0, 0, 0, 0, 0};
-  const double cell_HI = out_HI - in_HI, cell_HeI = out_HeI - in_HeI, cell_HeII = out_HeII - in_HeII;
-  const bool iso = d_run.isothermal != 0;
-  bool act[3];
-  int blo = NumFreqBnd + 1, bhi = 0;
-#pragma unroll
-  for (int s = 0; s < 3; s++) {
-    act[s] = (d_run.sed[s].hi >= d_run.sed[s].lo) && (nflux[s] > 0.0);
-    if (act[s]) { blo = min(blo, d_run.sed[s].lo); bhi = max(bhi, d_run.sed[s].hi); }
-  }
-  // secondary ionisation (Ricotti et al. 2002), :557-565 -- depends on the cell only
-  double y1R0 = 0, y1R1 = 0, y1R2 = 0, y2R0 = 0, y2R1 = 0, y2R2 = 0;
-  if (!iso) {
-    y1R0 = 0.3908 * pow(1.0 - pow(i_state, 0.4092), 1.7592);
-    y1R1 = 0.0554 * pow(1.0 - pow(i_state, 0.4614), 1.6660);
-    y1R2 = 1.0 * pow(1.0 - pow(i_state, 0.2663), 1.3163);
-    const double xeb01 = 1.0 - pow(i_state, 0.38);  // bR2(1) == bR2(2)
-    const double xeb2 = 1.0 - pow(i_state, 0.34);
-    const double p02 = pow(i_state, 0.2);            // aR2(1) == aR2(2)
-    y2R0 = 0.6941 * p02 * xeb01 * xeb01;
-    y2R1 = 0.0984 * p02 * xeb01 * xeb01;
-    y2R2 = 3.9811 * pow(i_state, 0.4) * xeb2 * xeb2;
-  }
-  double f_heat = 0.0, f_ion_HI = 0.0, f_ion_HeI = 0.0;
-
-  for (int b = blo; b <= bhi; b++) {  // 1-based band
-    const int q = b - 1;
-    const double sHI = d_band.sigma_HI[q], sHeI = d_band.sigma_HeI[q], sHeII = d_band.sigma_HeII[q];
-    const double tau_in = in_HI * sHI + in_HeI * sHeI + in_HeII * sHeII;     // :172-176
-    const double tau_out = out_HI * sHI + out_HeI * sHeI + out_HeII * sHeII;  // :179-183
-    const TauPos pin = tau_table_position(tau_in);
-    const double dtau = tau_out - tau_in;
-    const bool thick_p = fabs(dtau) > tau_photo_limit;
-    const bool thick_h = fabs(dtau) > tau_heat_limit;
-    TauPos pout;
-    if (thick_p) pout = tau_table_position(tau_out); else { pout.ipos = 0; pout.ipos_p1 = 0; pout.residual = 0; }
-    // species scalings :787-825 and per-species cell optical depths :236-240
-    const double tcHI = cell_HI * sHI, tcHeI = cell_HeI * sHeI, tcHeII = cell_HeII * sHeII;
-    double scHI = 1.0, scHeI = 0.0, scHeII = 0.0;
-    int hcol = 0, nsp = 1;
-    if (b > NumBndin1 + NumBndin2) {
-      const double f = 1.0 / (sHI * cell_HI + sHeI * cell_HeI + sHeII * cell_HeII);
-      scHI = tcHI * f; scHeI = tcHeI * f; scHeII = tcHeII * f;
-      hcol = 3 * b - NumBndin2 - NumBndin1 * 2 - 2 - 1; nsp = 3;
-    } else if (b > NumBndin1) {
-      const double f = 1.0 / (sHI * cell_HI + sHeI * cell_HeI);
-      scHI = sHI * cell_HI * f; scHeI = sHeI * cell_HeI * f;
-      hcol = 2 * b - NumBndin1 - 1 - 1; nsp = 2;
-    }
-    double ph_HI = 0.0, ph_HeI = 0.0, ph_HeII = 0.0;  // this band's heating per species, all SEDs
-#pragma unroll
-    for (int s = 0; s < 3; s++) {
-      if (!act[s] || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
-      const SedDev& T = d_run.sed[s];
-      const double NFlux = nflux[s];
-      const size_t off = (size_t)q * (NumTau + 1);
-      // photo_lookuptable :390-460
-      const double phi_in = NFlux * read_table(T.photo_thick + off, pin);
-      double phi_all, phi_out;
-      if (thick_p) {
-        phi_out = NFlux * read_table(T.photo_thick + off, pout);
-        phi_all = phi_in - phi_out;
-      } else {
-        phi_all = NFlux * dtau * read_table(T.photo_thin + off, pin);
-        phi_out = phi_in - phi_all;
-      }
-      r.photo_in += phi_in;
-      r.photo_out += phi_out;
-      r.photo_HI += scHI * phi_all / vol;
-      if (nsp >= 2) r.photo_HeI += scHeI * phi_all / vol;
-      if (nsp == 3) r.photo_HeII += scHeII * phi_all / vol;
-      // heat_lookuptable :586-760
-      if (!iso) {
-        const size_t ho = (size_t)hcol * (NumTau + 1);
-        if (thick_h) {
-          ph_HI += scHI * (NFlux * read_table(T.heat_thick + ho, pin) - NFlux * read_table(T.heat_thick + ho, pout)) / vol;
-          if (nsp >= 2)
-            ph_HeI += scHeI * (NFlux * read_table(T.heat_thick + ho + (NumTau + 1), pin) -
-                               NFlux * read_table(T.heat_thick + ho + (NumTau + 1), pout)) / vol;
-          if (nsp == 3)
-            ph_HeII += scHeII * (NFlux * read_table(T.heat_thick + ho + 2 * (NumTau + 1), pin) -
-                                 NFlux * read_table(T.heat_thick + ho + 2 * (NumTau + 1), pout)) / vol;
-        } else {
-          ph_HI += NFlux * tcHI * read_table(T.heat_thin + ho, pin) / vol;
-          if (nsp >= 2) ph_HeI += NFlux * tcHeI * read_table(T.heat_thin + ho + (NumTau + 1), pin) / vol;
-          if (nsp == 3) ph_HeII += NFlux * tcHeII * read_table(T.heat_thin + ho + 2 * (NumTau + 1), pin) / vol;
-        }
-      }
-    }
-    if (!iso) {
-      // the secondary-ionisation bookkeeping is linear in the per-species heating, so the SED sum can be
-      // taken first (:654-669, :739-759)
-      double df_heat = ph_HI + ph_HeI + ph_HeII;
-      if (b > NumBndin1) {
-        const double fs1 = d_band.f1ion_HI[q] * ph_HI + d_band.f1ion_HeI[q] * ph_HeI + d_band.f1ion_HeII[q] * ph_HeII;
-        const double fs2 = d_band.f2ion_HI[q] * ph_HI + d_band.f2ion_HeI[q] * ph_HeI + d_band.f2ion_HeII[q] * ph_HeII;
-        const double fs3 = d_band.f1heat_HI[q] * ph_HI + d_band.f1heat_HeI[q] * ph_HeI + d_band.f1heat_HeII[q] * ph_HeII;
-        const double fs4 = d_band.f2heat_HI[q] * ph_HI + d_band.f2heat_HeI[q] * ph_HeI + d_band.f2heat_HeII[q] * ph_HeII;
-        f_ion_HeI += y1R1 * fs1 - y2R1 * fs2;
-        f_ion_HI += y1R0 * fs1 - y2R0 * fs2;
-        df_heat = df_heat - y1R2 * fs3 + y2R2 * fs4;
-      }
-      f_heat += df_heat;
-    }
-  }
-  if (!iso) {
-    r.heat = f_heat;
-    r.photo_HI += f_ion_HI / (ion_freq_HI * hplanck);
-    r.photo_HeI += f_ion_HeI / (ion_freq_HeI * hplanck);
-  }
-  return r;
-}
-
 // column_density.f90:351-376
 __device__ __forceinline__ double weightf(double cd, double sig) { return 1.0 / fmax(0.6, cd * sig); }
 
