@@ -90,6 +90,7 @@ struct c2ray_ctx {
   double* tab[3][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
   int lo[3] = {1, 1, 1}, hi[3] = {0, 0, 0};
   double S_star[3] = {0, 0, 0};
+  double* packed[3] = {nullptr, nullptr, nullptr};
   TableBuild* d_tb = nullptr;
   // cooling
   double* d_cool = nullptr;
@@ -136,6 +137,7 @@ int bind(c2ray_ctx* c) {
   for (int s = 0; s < 3; s++) {
     rc.sed[s].photo_thick = c->tab[s][0]; rc.sed[s].photo_thin = c->tab[s][1];
     rc.sed[s].heat_thick = c->tab[s][2]; rc.sed[s].heat_thin = c->tab[s][3];
+    rc.sed[s].packed = c->packed[s];
     rc.sed[s].lo = c->lo[s]; rc.sed[s].hi = c->tab[s][0] ? c->hi[s] : c->lo[s] - 1;
     rc.sed[s].S_star = c->S_star[s];
   }
@@ -416,6 +418,7 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
                   c->d_slots, c->d_active, c->d_tot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
+  for (int s = 0; s < 3; s++) if (c->packed[s]) cudaFree(c->packed[s]);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_timer) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->stream);
@@ -444,6 +447,20 @@ int c2ray_b200_set_cooling_tables(c2ray_ctx* c, const double* logT, const double
   return C2RAY_OK;
 }
 
+static int pack_tables(c2ray_ctx* c, int s) {
+  if (!c->tab[s][0]) {
+    if (c->packed[s]) { cudaFree(c->packed[s]); c->packed[s] = nullptr; }
+    return 0;
+  }
+  const size_t n = (size_t)NumFreqBnd * PK_ROWS * PK_ROW;
+  if (!c->packed[s]) CK(cudaMalloc(&c->packed[s], n * sizeof(double)));
+  const int items = NumFreqBnd * PK_ROWS;
+  LAUNCH(c, k_pack_tables, (items + 255) / 256, 256, c->tab[s][0], c->tab[s][1], c->tab[s][2], c->tab[s][3], c->packed[s]);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 static int ensure_tables(c2ray_ctx* c, int s, bool heat) {
   const size_t np = (size_t)NumFreqBnd * (NumTau + 1), nh = (size_t)NumheatBin * (NumTau + 1);
   for (int k = 0; k < 4; k++) {
@@ -463,7 +480,7 @@ int c2ray_b200_upload_tables(c2ray_ctx* c, int32_t s, const c2ray_sed_tables* t)
   if (!t->photo_thick) {  // SED absent
     for (int k = 0; k < 4; k++) if (c->tab[s][k]) { cudaFree(c->tab[s][k]); c->tab[s][k] = nullptr; }
     c->lo[s] = 1; c->hi[s] = 0;
-    return C2RAY_OK;
+    return pack_tables(c, s);
   }
   if (!t->photo_thin) return fail(C2RAY_ERR_ARG, "photo_thin missing");
   const bool heat = t->heat_thick && t->heat_thin;
@@ -478,7 +495,7 @@ int c2ray_b200_upload_tables(c2ray_ctx* c, int32_t s, const c2ray_sed_tables* t)
     CK(cudaMemcpy(c->tab[s][3], t->heat_thin, nh, cudaMemcpyHostToDevice));
   }
   c->lo[s] = t->freqbnd_lower; c->hi[s] = t->freqbnd_upper; c->S_star[s] = t->S_star;
-  return C2RAY_OK;
+  return pack_tables(c, s);
 }
 
 int c2ray_b200_download_table(c2ray_ctx* c, int32_t s, int32_t kind, double* out, int32_t* lower, int32_t* upper,
@@ -564,6 +581,10 @@ int c2ray_b200_rad_ini(c2ray_ctx* c, const c2ray_sed_params* sp) {
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   c->run_dirty = true;
+  for (int s = 0; s < 3; s++) {
+    int rc = pack_tables(c, s);
+    if (rc) return rc;
+  }
   return C2RAY_OK;
 }
 

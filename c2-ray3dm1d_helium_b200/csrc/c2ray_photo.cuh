@@ -1,19 +1,32 @@
 // c2ray_photo.cuh -- radiation_photoionrates.f90:108-277 photoion_rates for one cell, streamed over the frequency
 // bands (no 47-element work arrays), written for instruction count: the round-1 profile showed 22.8 k warp
 // instructions per source x cell update of which only a third were FP64 arithmetic -- the rest came from IEEE
-// division slow-path scaffolding, the general-purpose log10/pow, and per-band divisions by the shell volume.
-//   * 1/vol, NFlux and 1/(x n abundance) are applied once per cell, not per band (all rates are linear in them)
-//   * (log10(tau)-minlogtau)/dlogtau becomes one FMA with 1/dlogtau
+// division slow-path scaffolding, the general-purpose log10/pow, per-band divisions by the shell volume and scalar
+// gathers from 16 different table columns per band.
+//   * 1/vol is applied once per cell, not per band (all rates are linear in it)
+//   * (log10(tau)-minlogtau)/dlogtau becomes one FMA with 1/dlogtau; the clamps of odpos move to the integer index
 //   * log10 is a branch-free atanh-series evaluation valid for the positive normal arguments that occur here
-//     (tau clamped to >= 1e-20), accurate to ~2e-16 relative
+//     (tau clamped to >= 1e-20), accurate to ~2e-16 relative, coefficients as constant-bank operands
 //   * reciprocals use MUFU.RCP64H + cubic/Newton refinement (error ~ 2^-54) without the IEEE slow path
 //   * the secondary-ionisation factors y1R, y2R (9 pow per cell in the reference, :557-565) depend on the cell only
 //     and are precomputed once per iteration by k_secion_factors
+//   * the four tables of an SED are re-packed band-major into 64-byte rows
+//       row(band, itau) = [photo_thick, heat_thick(HI,HeI,HeII), photo_thin, heat_thin(HI,HeI,HeII)]
+//     so one table position is two adjacent rows (128 contiguous bytes, 16-byte vector loads) instead of up to 16
+//     scalar gathers from different columns; row NumTau+1 duplicates row NumTau (ipos_p1 = min(NumTau, ipos+1))
+//   * the band loop is split by band group (1 / 26 / 20 sub-bands) with the species count as a template parameter
 // All of this changes results at the 1e-15 level; the parity tests hold 1e-8.
 #pragma once
 #include "c2ray_physics.cuh"
 
 namespace c2 {
+
+constexpr int PK_ROW = 8;                 // doubles per packed row
+constexpr int PK_ROWS = NumTau + 2;       // rows per band (one duplicate at the end)
+
+// 1/(2k+1), k = 9..1 : atanh series
+__constant__ double d_logc[9] = {1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0,
+                                 1.0 / 9.0,  1.0 / 7.0,  1.0 / 5.0,  1.0 / 3.0};
 
 // reciprocal without the IEEE special-case path; |rel err| ~ 2^-54 for normal b
 __device__ __forceinline__ double fast_rcp(double b) {
@@ -38,20 +51,13 @@ __device__ __forceinline__ double fast_log10(double x) {
   hi -= big << 20;                   // m *= 0.5
   e += big;
   const double m = __hiloint2double(hi, lo);
-  const double f = m - 1.0;
-  const double s = f * fast_rcp(m + 1.0);
+  const double s = (m - 1.0) * fast_rcp(m + 1.0);
   const double z = s * s;
-  double p = 1.0 / 19.0;
-  p = fma(p, z, 1.0 / 17.0);
-  p = fma(p, z, 1.0 / 15.0);
-  p = fma(p, z, 1.0 / 13.0);
-  p = fma(p, z, 1.0 / 11.0);
-  p = fma(p, z, 1.0 / 9.0);
-  p = fma(p, z, 1.0 / 7.0);
-  p = fma(p, z, 1.0 / 5.0);
-  p = fma(p, z, 1.0 / 3.0);
-  p = p * z;                                   // atanh(s)/s - 1
-  const double l = fma(s, p, s);               // atanh(s)
+  double p = d_logc[0];
+#pragma unroll
+  for (int k = 1; k < 9; k++) p = fma(p, z, d_logc[k]);
+  p = p * z;                      // atanh(s)/s - 1
+  const double l = fma(s, p, s);  // atanh(s)
   // log10(x) = e*log10(2) + 2*atanh(s)*log10(e)
   return fma((double)e, 0.30102999566398119521, l * 0.86858896380650365530);
 }
@@ -61,20 +67,20 @@ __device__ __forceinline__ double weightf_fast(double cd, double sig) { return f
 
 struct TauPos { int ipos; double residual; };
 
-__device__ __forceinline__ TauPos tau_table_position(double tau) {  // :282-306
+// radiation_photoionrates.f90:282-306: odpos = min(NumTau, max(0, 1+(log10(max(1e-20,tau))-minlogtau)/dlogtau)).
+// With tau >= 1e-20 the lower clamp never binds; the upper one is applied to the integer index: for odpos > NumTau
+// both interpolation rows are row NumTau, so the residual is irrelevant.
+__device__ __forceinline__ TauPos tau_table_position(double tau) {
   const double lt = fast_log10(fmax(1.0e-20, tau));
-  // odpos = min(NumTau, max(0, 1 + (lt - minlogtau)/dlogtau))
-  const double odpos = fmin((double)NumTau, fmax(0.0, fma(lt - minlogtau, 1.0 / dlogtau, 1.0)));
+  const double odpos = fma(lt - minlogtau, 1.0 / dlogtau, 1.0);
   TauPos p;
-  p.ipos = (int)odpos;
+  p.ipos = min((int)odpos, NumTau);
   p.residual = odpos - (double)p.ipos;
   return p;
 }
-// :310-326 ; ipos_p1 = min(NumTau, ipos+1): at ipos == NumTau the residual is 0, so re-reading row ipos is exact
-__device__ __forceinline__ double read_table(const double* __restrict__ col, const TauPos& p) {
-  const double a = __ldg(col + p.ipos), b = __ldg(col + min(NumTau, p.ipos + 1));
-  return fma(b - a, p.residual, a);
-}
+
+__device__ __forceinline__ double2 ld2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ double lerp(double a, double b, double t) { return fma(b - a, t, a); }  // :321-324
 
 struct PhotOut { double photo_HI, photo_HeI, photo_HeII, heat, photo_in, photo_out; };
 
@@ -94,12 +100,125 @@ __device__ __forceinline__ SecIon secion_factors(double i_state) {
   return y;
 }
 
+struct PhotAcc {  // per-cell accumulators, still to be multiplied by 1/vol (except a_in, a_out)
+  double a_in, a_out, a_HI, a_HeI, a_HeII, f_heat, f_ion_HI, f_ion_HeI;
+};
+
+struct CellCols {
+  double in_HI, in_HeI, in_HeII, out_HI, out_HeI, out_HeII, cell_HI, cell_HeI, cell_HeII;
+};
+
+// One frequency band (1-based b, NSP species absorb in it) for every active SED.
+template <bool ISO, int NSP>
+__device__ __forceinline__ void band_step(int b, const CellCols& c, const double nflux[3], const bool act[3],
+                                          const SecIon& y, PhotAcc& A) {
+  const int q = b - 1;
+  const double sHI = d_band.sigma_HI[q];
+  const double sHeI = NSP >= 2 ? d_band.sigma_HeI[q] : 0.0;
+  const double sHeII = NSP == 3 ? d_band.sigma_HeII[q] : 0.0;
+  double tau_in = c.in_HI * sHI, tau_out = c.out_HI * sHI;             // :172-183
+  if (NSP >= 2) { tau_in = fma(c.in_HeI, sHeI, tau_in); tau_out = fma(c.out_HeI, sHeI, tau_out); }
+  if (NSP == 3) { tau_in = fma(c.in_HeII, sHeII, tau_in); tau_out = fma(c.out_HeII, sHeII, tau_out); }
+  const double dtau = tau_out - tau_in;
+  const bool thick_p = fabs(dtau) > tau_photo_limit;
+  const bool thick_h = fabs(dtau) > tau_heat_limit;
+  const TauPos pin = tau_table_position(tau_in);
+  TauPos pout = pin;
+  if (thick_p) pout = tau_table_position(tau_out);
+  // species shares of the band's absorption (:787-825) and per-species cell optical depths (:236-240)
+  const double tcHI = c.cell_HI * sHI, tcHeI = c.cell_HeI * sHeI, tcHeII = c.cell_HeII * sHeII;
+  double scHI = 1.0, scHeI = 0.0, scHeII = 0.0;
+  if (NSP == 3) {
+    const double f = fast_rcp(tcHI + tcHeI + tcHeII);
+    scHI = tcHI * f; scHeI = tcHeI * f; scHeII = tcHeII * f;
+  } else if (NSP == 2) {
+    const double f = fast_rcp(tcHI + tcHeI);
+    scHI = tcHI * f; scHeI = tcHeI * f;
+  }
+  double phot = 0.0;                                  // absorbed photons of this band, all SEDs
+  double ph_HI = 0.0, ph_HeI = 0.0, ph_HeII = 0.0;    // heating per species of this band, all SEDs
+  const size_t row_in = ((size_t)q * PK_ROWS + pin.ipos) * PK_ROW;
+  const size_t row_out = ((size_t)q * PK_ROWS + pout.ipos) * PK_ROW;
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    if (!act[s] || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
+    const double* __restrict__ pk = d_run.sed[s].packed;
+    const double NFlux = nflux[s];
+    const double* ri = pk + row_in;
+    const double* ro = pk + row_out;
+    // thick values at tau_in: [photo_thick, heat_thick HI | heat_thick HeI, heat_thick HeII]
+    const double2 i0a = ld2(ri), i1a = ld2(ri + PK_ROW);
+    const double phi_in = NFlux * lerp(i0a.x, i1a.x, pin.residual);  // photo_lookuptable :390-396
+    double phi_all, phi_out;
+    double2 o0a = i0a, o1a = i1a;
+    if (thick_p) {
+      o0a = ld2(ro); o1a = ld2(ro + PK_ROW);
+      phi_out = NFlux * lerp(o0a.x, o1a.x, pout.residual);
+      phi_all = phi_in - phi_out;
+    } else {
+      const double thin = lerp(__ldg(ri + 4), __ldg(ri + PK_ROW + 4), pin.residual);
+      phi_all = NFlux * dtau * thin;
+      phi_out = phi_in - phi_all;
+    }
+    A.a_in += phi_in;
+    A.a_out += phi_out;
+    phot += phi_all;
+    if (!ISO) {  // heat_lookuptable :586-760
+      if (thick_h) {
+        ph_HI = fma(scHI, NFlux * (lerp(i0a.y, i1a.y, pin.residual) - lerp(o0a.y, o1a.y, pout.residual)), ph_HI);
+        if (NSP >= 2) {
+          const double2 i0b = ld2(ri + 2), i1b = ld2(ri + PK_ROW + 2), o0b = ld2(ro + 2), o1b = ld2(ro + PK_ROW + 2);
+          ph_HeI = fma(scHeI, NFlux * (lerp(i0b.x, i1b.x, pin.residual) - lerp(o0b.x, o1b.x, pout.residual)), ph_HeI);
+          if (NSP == 3)
+            ph_HeII = fma(scHeII, NFlux * (lerp(i0b.y, i1b.y, pin.residual) - lerp(o0b.y, o1b.y, pout.residual)), ph_HeII);
+        }
+      } else {
+        // thin rows at tau_in: [photo_thin, heat_thin HI | heat_thin HeI, heat_thin HeII]
+        const double2 t0a = ld2(ri + 4), t1a = ld2(ri + PK_ROW + 4);
+        ph_HI = fma(NFlux * tcHI, lerp(t0a.y, t1a.y, pin.residual), ph_HI);
+        if (NSP >= 2) {
+          const double2 t0b = ld2(ri + 6), t1b = ld2(ri + PK_ROW + 6);
+          ph_HeI = fma(NFlux * tcHeI, lerp(t0b.x, t1b.x, pin.residual), ph_HeI);
+          if (NSP == 3) ph_HeII = fma(NFlux * tcHeII, lerp(t0b.y, t1b.y, pin.residual), ph_HeII);
+        }
+      }
+    }
+  }
+  A.a_HI = fma(scHI, phot, A.a_HI);                  // :428-456
+  if (NSP >= 2) A.a_HeI = fma(scHeI, phot, A.a_HeI);
+  if (NSP == 3) A.a_HeII = fma(scHeII, phot, A.a_HeII);
+  if (!ISO) {
+    // the secondary-ionisation bookkeeping is linear in the per-species heating, so the SED sum is taken first
+    // (:654-669, :739-759)
+    double df_heat = ph_HI + ph_HeI + ph_HeII;
+    if (NSP >= 2) {
+      double fs1 = d_band.f1ion_HI[q] * ph_HI + d_band.f1ion_HeI[q] * ph_HeI;
+      double fs2 = d_band.f2ion_HI[q] * ph_HI + d_band.f2ion_HeI[q] * ph_HeI;
+      double fs3 = d_band.f1heat_HI[q] * ph_HI + d_band.f1heat_HeI[q] * ph_HeI;
+      double fs4 = d_band.f2heat_HI[q] * ph_HI + d_band.f2heat_HeI[q] * ph_HeI;
+      if (NSP == 3) {
+        fs1 = fma(d_band.f1ion_HeII[q], ph_HeII, fs1);
+        fs2 = fma(d_band.f2ion_HeII[q], ph_HeII, fs2);
+        fs3 = fma(d_band.f1heat_HeII[q], ph_HeII, fs3);
+        fs4 = fma(d_band.f2heat_HeII[q], ph_HeII, fs4);
+      }
+      A.f_ion_HeI += y.y1R1 * fs1 - y.y2R1 * fs2;
+      A.f_ion_HI += y.y1R0 * fs1 - y.y2R0 * fs2;
+      df_heat = df_heat - y.y1R2 * fs3 + y.y2R2 * fs4;
+    }
+    A.f_heat += df_heat;
+  }
+}
+
 // vol: the shell-cell volume the rates are diluted over; nflux: NormFlux, NormFluxPL, NormFluxQPL of the source.
 template <bool ISO>
 __device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, double in_HeI, double out_HeI,
                                                   double in_HeII, double out_HeII, double vol, const double nflux[3],
                                                   const SecIon& y) {
-  const double cell_HI = out_HI - in_HI, cell_HeI = out_HeI - in_HeI, cell_HeII = out_HeII - in_HeII;
+  CellCols c;
+  c.in_HI = in_HI; c.in_HeI = in_HeI; c.in_HeII = in_HeII;
+  c.out_HI = out_HI; c.out_HeI = out_HeI; c.out_HeII = out_HeII;
+  c.cell_HI = out_HI - in_HI; c.cell_HeI = out_HeI - in_HeI; c.cell_HeII = out_HeII - in_HeII;  // :167-169
   bool act[3];
   int blo = NumFreqBnd + 1, bhi = 0;
 #pragma unroll
@@ -107,103 +226,44 @@ __device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, d
     act[s] = (d_run.sed[s].hi >= d_run.sed[s].lo) && (nflux[s] > 0.0);
     if (act[s]) { blo = min(blo, d_run.sed[s].lo); bhi = max(bhi, d_run.sed[s].hi); }
   }
-  // accumulators, all still to be multiplied by 1/vol
-  double a_in = 0.0, a_out = 0.0, a_HI = 0.0, a_HeI = 0.0, a_HeII = 0.0;
-  double f_heat = 0.0, f_ion_HI = 0.0, f_ion_HeI = 0.0;
-
-  for (int b = blo; b <= bhi; b++) {  // 1-based band
-    const int q = b - 1;
-    const double sHI = d_band.sigma_HI[q], sHeI = d_band.sigma_HeI[q], sHeII = d_band.sigma_HeII[q];
-    const double tau_in = in_HI * sHI + in_HeI * sHeI + in_HeII * sHeII;     // :172-176
-    const double tau_out = out_HI * sHI + out_HeI * sHeI + out_HeII * sHeII;  // :179-183
-    const double dtau = tau_out - tau_in;
-    const bool thick_p = fabs(dtau) > tau_photo_limit;
-    const bool thick_h = fabs(dtau) > tau_heat_limit;
-    const TauPos pin = tau_table_position(tau_in);
-    TauPos pout = pin;
-    if (thick_p) pout = tau_table_position(tau_out);
-    // species shares of the band's absorption (:787-825) and per-species cell optical depths (:236-240)
-    const double tcHI = cell_HI * sHI, tcHeI = cell_HeI * sHeI, tcHeII = cell_HeII * sHeII;
-    int nsp = 1, hcol = 0;
-    double scHI = 1.0, scHeI = 0.0, scHeII = 0.0;
-    if (b > NumBndin1 + NumBndin2) {
-      const double f = fast_rcp(tcHI + tcHeI + tcHeII);
-      scHI = tcHI * f; scHeI = tcHeI * f; scHeII = tcHeII * f;
-      nsp = 3; hcol = 3 * b - NumBndin2 - NumBndin1 * 2 - 3;
-    } else if (b > NumBndin1) {
-      const double f = fast_rcp(tcHI + tcHeI);
-      scHI = tcHI * f; scHeI = tcHeI * f;
-      nsp = 2; hcol = 2 * b - NumBndin1 - 2;
-    }
-    double phot = 0.0;                                  // this band's absorbed photons, all SEDs
-    double ph_HI = 0.0, ph_HeI = 0.0, ph_HeII = 0.0;    // this band's heating per species, all SEDs
-#pragma unroll
-    for (int s = 0; s < 3; s++) {
-      if (!act[s] || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
-      const SedDev& T = d_run.sed[s];
-      const double NFlux = nflux[s];
-      const size_t off = (size_t)q * (NumTau + 1);
-      // photo_lookuptable :390-460
-      const double phi_in = NFlux * read_table(T.photo_thick + off, pin);
-      double phi_all, phi_out;
-      if (thick_p) {
-        phi_out = NFlux * read_table(T.photo_thick + off, pout);
-        phi_all = phi_in - phi_out;
-      } else {
-        phi_all = NFlux * dtau * read_table(T.photo_thin + off, pin);
-        phi_out = phi_in - phi_all;
-      }
-      a_in += phi_in;
-      a_out += phi_out;
-      phot += phi_all;
-      // heat_lookuptable :586-760
-      if (!ISO) {
-        const double* ht = T.heat_thick + (size_t)hcol * (NumTau + 1);
-        const double* hn = T.heat_thin + (size_t)hcol * (NumTau + 1);
-        if (thick_h) {
-          ph_HI += scHI * (NFlux * (read_table(ht, pin) - read_table(ht, pout)));
-          if (nsp >= 2) ph_HeI += scHeI * (NFlux * (read_table(ht + (NumTau + 1), pin) - read_table(ht + (NumTau + 1), pout)));
-          if (nsp == 3) ph_HeII += scHeII * (NFlux * (read_table(ht + 2 * (NumTau + 1), pin) - read_table(ht + 2 * (NumTau + 1), pout)));
-        } else {
-          ph_HI += NFlux * tcHI * read_table(hn, pin);
-          if (nsp >= 2) ph_HeI += NFlux * tcHeI * read_table(hn + (NumTau + 1), pin);
-          if (nsp == 3) ph_HeII += NFlux * tcHeII * read_table(hn + 2 * (NumTau + 1), pin);
-        }
-      }
-    }
-    a_HI = fma(scHI, phot, a_HI);
-    a_HeI = fma(scHeI, phot, a_HeI);
-    a_HeII = fma(scHeII, phot, a_HeII);
-    if (!ISO) {
-      // the secondary-ionisation bookkeeping is linear in the per-species heating, so the SED sum is taken first
-      // (:654-669, :739-759)
-      double df_heat = ph_HI + ph_HeI + ph_HeII;
-      if (b > NumBndin1) {
-        const double fs1 = d_band.f1ion_HI[q] * ph_HI + d_band.f1ion_HeI[q] * ph_HeI + d_band.f1ion_HeII[q] * ph_HeII;
-        const double fs2 = d_band.f2ion_HI[q] * ph_HI + d_band.f2ion_HeI[q] * ph_HeI + d_band.f2ion_HeII[q] * ph_HeII;
-        const double fs3 = d_band.f1heat_HI[q] * ph_HI + d_band.f1heat_HeI[q] * ph_HeI + d_band.f1heat_HeII[q] * ph_HeII;
-        const double fs4 = d_band.f2heat_HI[q] * ph_HI + d_band.f2heat_HeI[q] * ph_HeI + d_band.f2heat_HeII[q] * ph_HeII;
-        f_ion_HeI += y.y1R1 * fs1 - y.y2R1 * fs2;
-        f_ion_HI += y.y1R0 * fs1 - y.y2R0 * fs2;
-        df_heat = df_heat - y.y1R2 * fs3 + y.y2R2 * fs4;
-      }
-      f_heat += df_heat;
-    }
-  }
+  PhotAcc A = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (blo <= NumBndin1) band_step<ISO, 1>(1, c, nflux, act, y, A);
+  for (int b = max(blo, NumBndin1 + 1); b <= min(bhi, NumBndin1 + NumBndin2); b++) band_step<ISO, 2>(b, c, nflux, act, y, A);
+  for (int b = max(blo, NumBndin1 + NumBndin2 + 1); b <= bhi; b++) band_step<ISO, 3>(b, c, nflux, act, y, A);
   const double rvol = fast_rcp(vol);
   PhotOut r;
-  r.photo_in = a_in;
-  r.photo_out = a_out;
-  r.photo_HI = a_HI * rvol;
-  r.photo_HeI = a_HeI * rvol;
-  r.photo_HeII = a_HeII * rvol;
+  r.photo_in = A.a_in;
+  r.photo_out = A.a_out;
+  r.photo_HI = A.a_HI * rvol;
+  r.photo_HeI = A.a_HeI * rvol;
+  r.photo_HeII = A.a_HeII * rvol;
   r.heat = 0.0;
   if (!ISO) {
-    r.heat = f_heat * rvol;
-    r.photo_HI += f_ion_HI * rvol * (1.0 / (ion_freq_HI * hplanck));
-    r.photo_HeI += f_ion_HeI * rvol * (1.0 / (ion_freq_HeI * hplanck));
+    r.heat = A.f_heat * rvol;
+    r.photo_HI += A.f_ion_HI * rvol * (1.0 / (ion_freq_HI * hplanck));     // :773-777
+    r.photo_HeI += A.f_ion_HeI * rvol * (1.0 / (ion_freq_HeI * hplanck));
   }
   return r;
+}
+
+// Re-pack the four (0:NumTau, 1:nb) tables of one SED into band-major 64-byte rows.  One thread per (band, row).
+__global__ void k_pack_tables(const double* __restrict__ photo_thick, const double* __restrict__ photo_thin,
+                              const double* __restrict__ heat_thick, const double* __restrict__ heat_thin,
+                              double* __restrict__ packed) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NumFreqBnd * PK_ROWS) return;
+  const int q = t / PK_ROWS, row = t % PK_ROWS, it = min(row, NumTau), b = q + 1;
+  const int nsp = (b <= NumBndin1) ? 1 : (b <= NumBndin1 + NumBndin2 ? 2 : 3);
+  const int hcol = (b <= NumBndin1) ? 0 : (b <= NumBndin1 + NumBndin2 ? 2 * b - NumBndin1 - 2 : 3 * b - NumBndin2 - NumBndin1 * 2 - 3);
+  double v[PK_ROW] = {0, 0, 0, 0, 0, 0, 0, 0};
+  v[0] = photo_thick[(size_t)q * (NumTau + 1) + it];
+  v[4] = photo_thin[(size_t)q * (NumTau + 1) + it];
+  if (heat_thick && heat_thin)
+    for (int sp = 0; sp < nsp; sp++) {
+      v[1 + sp] = heat_thick[(size_t)(hcol + sp) * (NumTau + 1) + it];
+      v[5 + sp] = heat_thin[(size_t)(hcol + sp) * (NumTau + 1) + it];
+    }
+  for (int k = 0; k < PK_ROW; k++) packed[(size_t)t * PK_ROW + k] = v[k];
 }
 
 }  // namespace c2

@@ -18,6 +18,7 @@ struct SedDev {
   const double* photo_thin;
   const double* heat_thick;   // [heatbin][0:NumTau]
   const double* heat_thin;
+  const double* packed;       // the same four tables as band-major 64-byte rows (c2ray_photo.cuh)
   int lo, hi;                 // 1-based FreqBnd limits (hi < lo : SED absent)
   double S_star;
 };
