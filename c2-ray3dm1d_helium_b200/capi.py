@@ -5,7 +5,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libc2ray_b200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("C2RAY_B200_LIB", "libc2ray_b200.so"))  # env override: tuning builds only
 CSRC = os.path.join(HERE, "csrc")
 
 NUMFREQBND, NUMHEATBIN, NUMTAU, MAX_ITER_HIST = 47, 113, 2000, 512

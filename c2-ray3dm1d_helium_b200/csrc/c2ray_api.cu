@@ -284,6 +284,7 @@ int sweep_all(c2ray_ctx* c) {
     GridPtrs G{c->ndens, c->xh_av, c->xhe_av, c->rates, c->d_secion, c->N3};
     const int batch = c->par.deterministic ? 1 : c->slots_cap;
     const int max_blocks = 148 * 16;
+    const bool multi_sed = c->tab[1][0] != nullptr || c->tab[2][0] != nullptr;  // PL / QPL tables present
     for (int first = 0; first < c->n_mine; first += batch) {
       const int ns = std::min(batch, c->n_mine - first);
       LAUNCH(c, k_slots_init, (ns + 127) / 128, 128, c->d_slots, ns, c->d_srcids + first, c->d_srcpos, c->d_nf,
@@ -296,8 +297,10 @@ int sweep_all(c2ray_ctx* c) {
         for (int r = r_lo; r <= r_hi; r++) {
           const long long items = (long long)ns * (r == 0 ? 1 : 24LL * r * r + 2);
           const int blocks = (int)std::min<long long>((items + 127) / 128, max_blocks);
-          if (c->par.isothermal) LAUNCH(c, k_sweep_shell<true>, blocks, 128, c->d_slots, c->d_active, c->d_tot, g, G, c->d_scratch, r);
-          else LAUNCH(c, k_sweep_shell<false>, blocks, 128, c->d_slots, c->d_active, c->d_tot, g, G, c->d_scratch, r);
+#define SWEEP(ISO, MULTI) LAUNCH(c, (k_sweep_shell<ISO, MULTI>), blocks, 128, c->d_slots, c->d_active, c->d_tot, g, G, c->d_scratch, r)
+          if (multi_sed) { if (c->par.isothermal) SWEEP(true, true); else SWEEP(false, true); }
+          else { if (c->par.isothermal) SWEEP(true, false); else SWEEP(false, false); }
+#undef SWEEP
         }
         if ((long long)g.subboxsize * b >= reach3) break;  // the do-while's extent test fails for every source
       }

@@ -149,8 +149,11 @@ __global__ void k_secion_factors(const double* __restrict__ xh_av, size_t N3, do
 }
 
 // One shell radius r of every active source.  Work item = (active slot, cell of the shell).
-template <bool ISO>
-__global__ void __launch_bounds__(128)
+#ifndef C2RAY_SWEEP_MINBLOCKS
+#define C2RAY_SWEEP_MINBLOCKS 4
+#endif
+template <bool ISO, bool MULTI>
+__global__ void __launch_bounds__(128, C2RAY_SWEEP_MINBLOCKS)
 k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot, SweepGeom g,
               GridPtrs G, double* __restrict__ scratch, int r) {
   const int nact = tot->nactive;
@@ -280,7 +283,7 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
 
     PhotOut phi = {0, 0, 0, 0, 0, 0};
     if (cin_H < max_coldensh) {  // :250-270
-      phi = photoion_rates<ISO>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, vol_ph, S.nflux, yR);
+      phi = photoion_rates<ISO, MULTI>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, vol_ph, S.nflux, yR);
       phi.photo_HI = phi.photo_HI / (h_av0 * ndens_p * (1.0 - abu_he));
       phi.photo_HeI = phi.photo_HeI / (he_av0 * ndens_p * abu_he);
       phi.photo_HeII = phi.photo_HeII / (he_av1 * ndens_p * abu_he);
@@ -418,8 +421,8 @@ __global__ void k_photoion_batch(int n, const double* __restrict__ col6, const d
   const double* q = col6 + 6 * (size_t)t;
   const double nflux[3] = {nf0, nf1, nf2};
   const SecIon y = secion_factors(i_state[t]);
-  const PhotOut r = d_run.isothermal ? photoion_rates<true>(q[0], q[1], q[2], q[3], q[4], q[5], vol[t], nflux, y)
-                                     : photoion_rates<false>(q[0], q[1], q[2], q[3], q[4], q[5], vol[t], nflux, y);
+  const PhotOut r = d_run.isothermal ? photoion_rates<true, true>(q[0], q[1], q[2], q[3], q[4], q[5], vol[t], nflux, y)
+                                     : photoion_rates<false, true>(q[0], q[1], q[2], q[3], q[4], q[5], vol[t], nflux, y);
   double* o = out6 + 6 * (size_t)t;
   o[0] = r.photo_HI; o[1] = r.photo_HeI; o[2] = r.photo_HeII; o[3] = r.heat; o[4] = r.photo_in; o[5] = r.photo_out;
 }

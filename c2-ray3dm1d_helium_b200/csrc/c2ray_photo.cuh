@@ -53,9 +53,14 @@ __device__ __forceinline__ double fast_log10(double x) {
   const double m = __hiloint2double(hi, lo);
   const double s = (m - 1.0) * fast_rcp(m + 1.0);
   const double z = s * s;
-  double p = d_logc[0];
-#pragma unroll
-  for (int k = 1; k < 9; k++) p = fma(p, z, d_logc[k]);
+  // sum_{k=1..9} z^k/(2k+1), Estrin scheme (dependency depth 4 instead of 9)
+  const double z2 = z * z, z4 = z2 * z2;
+  const double q0 = fma(d_logc[7], z, d_logc[8]);   // 1/3 + z/5
+  const double q1 = fma(d_logc[5], z, d_logc[6]);   // 1/7 + z/9
+  const double q2 = fma(d_logc[3], z, d_logc[4]);   // 1/11 + z/13
+  const double q3 = fma(d_logc[1], z, d_logc[2]);   // 1/15 + z/17
+  const double r0 = fma(q1, z2, q0), r1 = fma(q3, z2, q2);
+  double p = fma(fma(d_logc[0], z4, r1), z4, r0);   // r0 + z4*(r1 + z4/19)
   p = p * z;                      // atanh(s)/s - 1
   const double l = fma(s, p, s);  // atanh(s)
   // log10(x) = e*log10(2) + 2*atanh(s)*log10(e)
@@ -109,7 +114,8 @@ struct CellCols {
 };
 
 // One frequency band (1-based b, NSP species absorb in it) for every active SED.
-template <bool ISO, int NSP>
+// MULTI = false: only the black-body SED exists in this run; NFlux is then factored out of the band loop.
+template <bool ISO, int NSP, bool MULTI>
 __device__ __forceinline__ void band_step(int b, const CellCols& c, const double nflux[3], const bool act[3],
                                           const SecIon& y, PhotAcc& A) {
   const int q = b - 1;
@@ -122,9 +128,10 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
   const double dtau = tau_out - tau_in;
   const bool thick_p = fabs(dtau) > tau_photo_limit;
   const bool thick_h = fabs(dtau) > tau_heat_limit;
+  // both positions unconditionally: the two log10 evaluations are independent and interleave (the thin branch, which
+  // does not need pout, is the rare one)
   const TauPos pin = tau_table_position(tau_in);
-  TauPos pout = pin;
-  if (thick_p) pout = tau_table_position(tau_out);
+  const TauPos pout = tau_table_position(tau_out);
   // species shares of the band's absorption (:787-825) and per-species cell optical depths (:236-240)
   const double tcHI = c.cell_HI * sHI, tcHeI = c.cell_HeI * sHeI, tcHeII = c.cell_HeII * sHeII;
   double scHI = 1.0, scHeI = 0.0, scHeII = 0.0;
@@ -140,10 +147,12 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
   const size_t row_in = ((size_t)q * PK_ROWS + pin.ipos) * PK_ROW;
   const size_t row_out = ((size_t)q * PK_ROWS + pout.ipos) * PK_ROW;
 #pragma unroll
-  for (int s = 0; s < 3; s++) {
-    if (!act[s] || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
+  for (int s = 0; s < (MULTI ? 3 : 1); s++) {
+    if (MULTI) {
+      if (!act[s] || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
+    }
     const double* __restrict__ pk = d_run.sed[s].packed;
-    const double NFlux = nflux[s];
+    const double NFlux = MULTI ? nflux[s] : 1.0;
     const double* ri = pk + row_in;
     const double* ro = pk + row_out;
     // thick values at tau_in: [photo_thick, heat_thick HI | heat_thick HeI, heat_thick HeII]
@@ -211,7 +220,7 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
 }
 
 // vol: the shell-cell volume the rates are diluted over; nflux: NormFlux, NormFluxPL, NormFluxQPL of the source.
-template <bool ISO>
+template <bool ISO, bool MULTI>
 __device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, double in_HeI, double out_HeI,
                                                   double in_HeII, double out_HeII, double vol, const double nflux[3],
                                                   const SecIon& y) {
@@ -219,21 +228,29 @@ __device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, d
   c.in_HI = in_HI; c.in_HeI = in_HeI; c.in_HeII = in_HeII;
   c.out_HI = out_HI; c.out_HeI = out_HeI; c.out_HeII = out_HeII;
   c.cell_HI = out_HI - in_HI; c.cell_HeI = out_HeI - in_HeI; c.cell_HeII = out_HeII - in_HeII;  // :167-169
-  bool act[3];
-  int blo = NumFreqBnd + 1, bhi = 0;
+  bool act[3] = {true, false, false};
+  int blo, bhi;
+  double scale = 1.0;
+  if (MULTI) {
+    blo = NumFreqBnd + 1; bhi = 0;
 #pragma unroll
-  for (int s = 0; s < 3; s++) {
-    act[s] = (d_run.sed[s].hi >= d_run.sed[s].lo) && (nflux[s] > 0.0);
-    if (act[s]) { blo = min(blo, d_run.sed[s].lo); bhi = max(bhi, d_run.sed[s].hi); }
+    for (int s = 0; s < 3; s++) {
+      act[s] = (d_run.sed[s].hi >= d_run.sed[s].lo) && (nflux[s] > 0.0);
+      if (act[s]) { blo = min(blo, d_run.sed[s].lo); bhi = max(bhi, d_run.sed[s].hi); }
+    }
+  } else {
+    blo = d_run.sed[0].lo; bhi = d_run.sed[0].hi;
+    scale = nflux[0];
+    if (!(scale > 0.0)) bhi = 0;  // :207 if (NormFlux(nsrc) > 0.0)
   }
   PhotAcc A = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (blo <= NumBndin1) band_step<ISO, 1>(1, c, nflux, act, y, A);
-  for (int b = max(blo, NumBndin1 + 1); b <= min(bhi, NumBndin1 + NumBndin2); b++) band_step<ISO, 2>(b, c, nflux, act, y, A);
-  for (int b = max(blo, NumBndin1 + NumBndin2 + 1); b <= bhi; b++) band_step<ISO, 3>(b, c, nflux, act, y, A);
-  const double rvol = fast_rcp(vol);
+  if (blo <= NumBndin1 && bhi >= 1) band_step<ISO, 1, MULTI>(1, c, nflux, act, y, A);
+  for (int b = max(blo, NumBndin1 + 1); b <= min(bhi, NumBndin1 + NumBndin2); b++) band_step<ISO, 2, MULTI>(b, c, nflux, act, y, A);
+  for (int b = max(blo, NumBndin1 + NumBndin2 + 1); b <= bhi; b++) band_step<ISO, 3, MULTI>(b, c, nflux, act, y, A);
+  const double rvol = fast_rcp(vol) * scale;
   PhotOut r;
-  r.photo_in = A.a_in;
-  r.photo_out = A.a_out;
+  r.photo_in = A.a_in * scale;
+  r.photo_out = A.a_out * scale;
   r.photo_HI = A.a_HI * rvol;
   r.photo_HeI = A.a_HeI * rvol;
   r.photo_HeII = A.a_HeII * rvol;
