@@ -152,7 +152,7 @@ int bind(c2ray_ctx* c) {
   rc.cosmo_coef = 0;
   for (int d = 0; d < 3; d++) { rc.dr[d] = c->dr[d]; rc.mesh[d] = c->mesh[d]; }
   rc.vol = c->vol;
-  rc.cool_mintemp = c->cool_mintemp; rc.cool_dtemp = c->cool_dtemp; rc.cool = c->d_cool;
+  rc.cool_mintemp = c->cool_mintemp; rc.cool_dtemp = c->cool_dtemp; rc.cool_rdtemp = 1.0 / c->cool_dtemp; rc.cool = c->d_cool;
   CK(cudaMemcpyToSymbolAsync(d_run, &rc, sizeof(rc), 0, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));  // rc is a stack object
   g_bound = c;

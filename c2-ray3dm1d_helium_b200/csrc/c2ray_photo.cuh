@@ -24,49 +24,6 @@ namespace c2 {
 constexpr int PK_ROW = 8;                 // doubles per packed row
 constexpr int PK_ROWS = NumTau + 2;       // rows per band (one duplicate at the end)
 
-// 1/(2k+1), k = 9..1 : atanh series
-__constant__ double d_logc[9] = {1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0,
-                                 1.0 / 9.0,  1.0 / 7.0,  1.0 / 5.0,  1.0 / 3.0};
-
-// reciprocal without the IEEE special-case path; |rel err| ~ 2^-54 for normal b
-__device__ __forceinline__ double fast_rcp(double b) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-  double e = fma(-b, r, 1.0);
-  e = fma(e, e, e);
-  r = fma(r, e, r);
-  e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-  return r;
-}
-
-// log10 for positive normal x (no zero / subnormal / inf / nan handling): x = 2^e * m, m in [sqrt(1/2), sqrt(2)),
-// log(m) = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716
-__device__ __forceinline__ double fast_log10(double x) {
-  int hi = __double2hiint(x);
-  const int lo = __double2loint(x);
-  int e = (hi >> 20) - 1023;
-  hi = (hi & 0x000fffff) | 0x3ff00000;
-  const int big = hi >= 0x3ff6a09f;  // m >= ~sqrt(2)
-  hi -= big << 20;                   // m *= 0.5
-  e += big;
-  const double m = __hiloint2double(hi, lo);
-  const double s = (m - 1.0) * fast_rcp(m + 1.0);
-  const double z = s * s;
-  // sum_{k=1..9} z^k/(2k+1), Estrin scheme (dependency depth 4 instead of 9)
-  const double z2 = z * z, z4 = z2 * z2;
-  const double q0 = fma(d_logc[7], z, d_logc[8]);   // 1/3 + z/5
-  const double q1 = fma(d_logc[5], z, d_logc[6]);   // 1/7 + z/9
-  const double q2 = fma(d_logc[3], z, d_logc[4]);   // 1/11 + z/13
-  const double q3 = fma(d_logc[1], z, d_logc[2]);   // 1/15 + z/17
-  const double r0 = fma(q1, z2, q0), r1 = fma(q3, z2, q2);
-  double p = fma(fma(d_logc[0], z4, r1), z4, r0);   // r0 + z4*(r1 + z4/19)
-  p = p * z;                      // atanh(s)/s - 1
-  const double l = fma(s, p, s);  // atanh(s)
-  // log10(x) = e*log10(2) + 2*atanh(s)*log10(e)
-  return fma((double)e, 0.30102999566398119521, l * 0.86858896380650365530);
-}
-
 // column_density.f90:351-376 with the fast reciprocal
 __device__ __forceinline__ double weightf_fast(double cd, double sig) { return fast_rcp(fmax(0.6, cd * sig)); }
 

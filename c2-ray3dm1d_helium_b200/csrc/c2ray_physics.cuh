@@ -7,6 +7,26 @@
 // per-SED loop.  Each function cites the reference lines whose arithmetic it must reproduce.
 #pragma once
 #include "c2ray_consts.cuh"
+#include "c2ray_fastmath.cuh"
+
+#ifndef C2RAY_FAST_COEF
+#define C2RAY_FAST_COEF 1
+#endif
+// doric's exponentials feed (e^x - 1)/x and differences of O(1) terms: libdevice exp (< 1 ulp near 1) keeps the
+// fractions at the 1.5e-11 noise level, the cheaper fast_exp (~2 ulp) measured 2.5e-10 for no gain in time.
+#ifndef C2RAY_DORIC_EXP
+#define C2RAY_DORIC_EXP exp
+#endif
+#ifndef C2RAY_DORIC_IEEE_DIV
+#define C2RAY_DORIC_IEEE_DIV 0
+#endif
+#if C2RAY_DORIC_IEEE_DIV
+#define DDIV(a, b) ((a) / (b))
+#define DDIVR(a, b, r) ((a) / (b))
+#else
+#define DDIV(a, b) fdiv((a), (b))
+#define DDIVR(a, b, r) fdiv_r((a), (b), (r))
+#endif
 
 namespace c2 {
 
@@ -39,7 +59,7 @@ struct RunConst {
   double cosmo_coef;      // 2.0/(1.0+zred)*dzdt  applied as e_int*2.0/(1.0+zred)*dzdt
   double zp1, dzdt;
   double dr[3], vol;
-  double cool_mintemp, cool_dtemp;
+  double cool_mintemp, cool_dtemp, cool_rdtemp;  // rdtemp = 1/dtemp
   const double* cool;     // 5 x 801 linear cooling tables: h0,h1,he0,he1,he2
   int mesh[3];
 };
@@ -61,6 +81,56 @@ struct Ion {
 // ------------------------------------------------------------------------------------------------
 // cgsconstants.f90:140-266 ini_rec_colion_factors (literal kinds reproduced, see FL())
 // ------------------------------------------------------------------------------------------------
+// The 13 pow() of the fits share four bases (lambda and T up to constant factors), so one log and one exp per term
+// replace them: x^p = exp(p ln x), ln(lambda_He) = ln(lambda_H) + ln(T_He/T_H), ln(T/1e4) = ln(2 T_H/1e4) - ln(lambda_H).
+// ln of the (binary32 / _dp) fit constants, to 20 digits:
+constexpr double LN_F0522 = -0.65008766278158320814;   // ln((double)0.522f)
+constexpr double LN_F2740 = 1.0079579238805420492;     // ln((double)2.740f)
+constexpr double LN_D0522 = -0.65008769109949833266;   // ln(0.522_dp)
+constexpr double LN_D2740 = 1.0079579203999788567;     // ln(2.740_dp)
+constexpr double LN_HE0_OVER_H = 0.59229515194333738436;  // ln(temphe(0)/temph0)
+constexpr double LN_HE1_OVER_H = 1.3867355433101860653;   // ln(temphe(1)/temph0)
+constexpr double LN_2TH0_OVER_1E4 = 3.4519179578675728116;  // ln(2*temph0/1e4)
+
+// lam^pA / (1 + (lam/div)^pB)^pC  with lnl = ln(lam), lnd = ln(div)
+__device__ __forceinline__ double hg_fit(double lnl, double lnd, double pA, double pB, double pC) {
+  const double u = fast_exp(pB * (lnl - lnd));
+  return fast_exp(fma(pA, lnl, -pC * fast_log(1.0 + u)));
+}
+
+#if C2RAY_FAST_COEF
+__device__ __forceinline__ void ini_rec_colion_factors(double T, RecCol& r) {
+  const double rT = fast_rcp(T);
+  const double lambda = 2.0 * (temph0 * rT);
+  const double lnl = fast_log(lambda);
+  // the H fit is shared by arech0/brech0 and (T<9e3) areche0/breche0 up to the leading literal
+  const double hA = hg_fit(lnl, LN_F0522, 1.503, FL(0.470f), FL(1.923f));
+  const double hB = hg_fit(lnl, LN_F2740, 1.500, FL(0.407f), FL(2.242f));
+  r.arech0 = FL(1.269e-13f) * hA;
+  r.brech0 = FL(2.753e-14f) * hB;
+  const double sqrtt0 = sqrt(T);
+  if (T < 9.e3) {
+    r.areche0 = 1.269e-13 * hA;
+    r.breche0 = 2.753e-14 * hB;
+  } else {
+    const double lnl0 = lnl + LN_HE0_OVER_H;  // lambda = 2*temphe(0)/T
+    const double dielectronic = 1.9e-3 * (rT * fast_rcp(sqrtt0)) * fast_exp(-4.7e5 * rT) * (1.0 + 0.3 * fast_exp(-9.4e4 * rT));
+    r.areche0 = 3.000e-14 * fast_exp(0.654 * lnl0) + dielectronic;
+    r.breche0 = 1.260e-14 * fast_exp(0.750 * lnl0) + dielectronic;
+  }
+  r.oreche0 = r.areche0 - r.breche0;
+  const double lnl1 = lnl + LN_HE1_OVER_H;    // lambda = 2*temphe(1)/T
+  r.breche1 = 5.5060e-14 * hg_fit(lnl1, LN_D2740, 1.5, 0.407, 2.242);
+  r.areche1 = FL(2.538e-13f) * hg_fit(lnl1, LN_D0522, 1.503, 0.470, 1.923);
+  const double lnt4 = LN_2TH0_OVER_1E4 - lnl;  // ln(T/1e4)
+  r.treche1 = 3.4e-13 * fast_exp(-0.6 * lnt4);
+  r.v = 0.285 * fast_exp(0.119 * lnt4);
+  r.colli_HI = colh0 * sqrtt0 * fast_exp(-temph0 * rT);
+  r.colli_HeI = colhe0 * sqrtt0 * fast_exp(-temphe0 * rT);
+  r.colli_HeII = colhe1 * sqrtt0 * fast_exp(-temphe1 * rT);
+}
+#else
+// libdevice pow/exp version (13 pow): 2x slower global pass; kept for A/B checks (-DC2RAY_FAST_COEF=0).
 __device__ __forceinline__ void ini_rec_colion_factors(double T, RecCol& r) {
   double lambda = 2.0 * (temph0 / T);
   // the H fit is shared by arech0/brech0 and (T<9e3) areche0/breche0 up to the leading literal
@@ -88,6 +158,7 @@ __device__ __forceinline__ void ini_rec_colion_factors(double T, RecCol& r) {
   r.colli_HeI = colhe0 * sqrtt0 * exp(-temphe0 / T);
   r.colli_HeII = colhe1 * sqrtt0 * exp(-temphe1 / T);
 }
+#endif
 
 // tped.f90:75-84
 __device__ __forceinline__ double electrondens(double n, double xh1, double xhe1, double xhe2) {
@@ -97,7 +168,7 @@ __device__ __forceinline__ double electrondens(double n, double xh1, double xhe1
 // cooling_h.f90:40-71
 __device__ __forceinline__ double coolin(double n, double ne, double h_av0, double h_av1, double he_av0, double he_av1,
                                          double he_av2, double T, const double* __restrict__ ct) {
-  const double tpos = (log10(T) - d_run.cool_mintemp) / d_run.cool_dtemp + 1.0;
+  const double tpos = fma(fast_log10(T) - d_run.cool_mintemp, d_run.cool_rdtemp, 1.0);
   const int itpos = min(TEMPPOINTS - 1, max(1, (int)tpos));
   const double dtpos = tpos - (double)itpos;
   const int a = itpos - 1, b = min(TEMPPOINTS, itpos + 1) - 1;
@@ -120,11 +191,12 @@ __device__ __forceinline__ DoricFrac prepare_doric_factors(double n, double h0, 
   const double tau_H_he2th = NH * sigma_H_he2, tau_He_he2th = NHe0 * sigma_He_he2;
   const double tau_He2_he2th = NHe1 * sigma_HeII_at_ion_freq;
   DoricFrac f;
-  f.y = tau_H_heth / (tau_H_heth + tau_He_heth);
-  f.z = tau_H_heLya / (tau_H_heLya + tau_He_heLya);
-  const double den = tau_He2_he2th + tau_He_he2th + tau_H_he2th;
-  f.y2a = tau_He2_he2th / den;
-  f.y2b = tau_He_he2th / den;
+  f.y = DDIV(tau_H_heth, tau_H_heth + tau_He_heth);
+  f.z = DDIV(tau_H_heLya, tau_H_heLya + tau_He_heLya);
+  const double dden = tau_He2_he2th + tau_He_he2th + tau_H_he2th;
+  const double rden = fast_rcp(dden);
+  f.y2a = DDIVR(tau_He2_he2th, dden, rden);
+  f.y2b = DDIVR(tau_He_he2th, dden, rden);
   return f;
 }
 
@@ -158,28 +230,31 @@ __device__ __forceinline__ void doric(double dt, double rhe, Ion& ion, double ph
                       alpha_he2_1 * fr.y2b * rhe;
   const double Bcoef = Emat - Pmat;
   const double Scoef = sqrt(Bcoef * Bcoef + 4.0 * aihe1 * Qmat);
-  const double QHEPcoef = 1.0 / (Qmat * aihe1 - Emat * Pmat);
+  const double QHEPcoef = DDIV(1.0, Qmat * aihe1 - Emat * Pmat);
   const double BminusS = Bcoef - Scoef, BplusS = Bcoef + Scoef;
   const double lambda1 = Lmat;
   const double lambda2 = 0.5 * (Emat + Pmat - Scoef);
   const double lambda3 = 0.5 * (Emat + Pmat + Scoef);
-  const double rx = -1.0 / Lmat * (aih0 + (Mmat * Emat - Nmat * aihe1) * (aihe0 * QHEPcoef));
+  const double rx = DDIV(-1.0, Lmat) * (aih0 + (Mmat * Emat - Nmat * aihe1) * (aihe0 * QHEPcoef));
   const double ry = aihe0 * (Emat * QHEPcoef);
   const double rz = -aihe0 * (aihe1 * QHEPcoef);
   const double twoaihe1 = 2.0 * aihe1;
-  const double eigv2x = -Nmat / (Lmat - lambda2) + (Mmat / twoaihe1) * BplusS / (Lmat - lambda2);
-  const double eigv3x = (-twoaihe1 * Nmat + Mmat * BminusS) / (twoaihe1 * (Lmat - lambda3));
-  const double eigv2y = (-BplusS) / twoaihe1;
-  const double eigv3y = (-BminusS) / twoaihe1;
+  // doric's coefficients are differences of large terms (noise amplification ~1e5): every
+  // quotient below is corrected to ~0.5 ulp so the GPU stays at the noise level of the reference's own arithmetic
+  const double dL2 = Lmat - lambda2, dL3t = twoaihe1 * (Lmat - lambda3), twoS = 2.0 * Scoef;
+  const double r2a = fast_rcp(twoaihe1), rL2 = fast_rcp(dL2), rL3t = fast_rcp(dL3t), r2S = fast_rcp(twoS);
+  const double eigv2x = DDIVR(-Nmat, dL2, rL2) + DDIVR(DDIVR(Mmat, twoaihe1, r2a) * BplusS, dL2, rL2);
+  const double eigv3x = DDIVR(-twoaihe1 * Nmat + Mmat * BminusS, dL3t, rL3t);
+  const double eigv2y = DDIVR(-BplusS, twoaihe1, r2a);
+  const double eigv3y = DDIVR(-BminusS, twoaihe1, r2a);
   const double Rcoef = twoaihe1 * (ry - ion.he_old1);
   const double Tcoef = rz - ion.he_old2;
-  const double twoS = 2.0 * Scoef;
-  const double coef2 = (Rcoef + BminusS * Tcoef) / twoS;
-  const double coef3 = -(Rcoef + BplusS * Tcoef) / twoS;
-  const double coef1 = -rx + (eigv3x - eigv2x) * (Rcoef / twoS) +
-                       Tcoef * (BplusS * eigv3x / twoS - BminusS * eigv2x / twoS) + ion.h_old1;
+  const double coef2 = DDIVR(Rcoef + BminusS * Tcoef, twoS, r2S);
+  const double coef3 = -DDIVR(Rcoef + BplusS * Tcoef, twoS, r2S);
+  const double coef1 = -rx + (eigv3x - eigv2x) * DDIVR(Rcoef, twoS, r2S) +
+                       Tcoef * (DDIVR(BplusS * eigv3x, twoS, r2S) - DDIVR(BminusS * eigv2x, twoS, r2S)) + ion.h_old1;
   const double lam1dt = dt * lambda1, lam2dt = dt * lambda2, lam3dt = dt * lambda3;
-  const double elam1dt = exp(lam1dt), elam2dt = exp(lam2dt), elam3dt = exp(lam3dt);
+  const double elam1dt = C2RAY_DORIC_EXP(lam1dt), elam2dt = C2RAY_DORIC_EXP(lam2dt), elam3dt = C2RAY_DORIC_EXP(lam3dt);
 
   ion.h1 = coef1 * elam1dt + coef2 * elam2dt * eigv2x + coef3 * elam3dt * eigv3x + rx;
   ion.he1 = coef2 * elam2dt * eigv2y + coef3 * elam3dt * eigv3y + ry;
@@ -196,9 +271,9 @@ __device__ __forceinline__ void doric(double dt, double rhe, Ion& ion, double ph
     ion.he0 = ion.he0 / normfac; ion.he1 = ion.he1 / normfac; ion.he2 = ion.he2 / normfac;
   }
   const double lim = FL(1.0e-8f);
-  const double af1 = (fabs(lam1dt) < lim) ? coef1 : coef1 * (elam1dt - 1.0) / lam1dt;
-  const double af2 = (fabs(lam2dt) < lim) ? coef2 : coef2 * (elam2dt - 1.0) / lam2dt;
-  const double af3 = (fabs(lam3dt) < lim) ? coef3 : coef3 * (elam3dt - 1.0) / lam3dt;
+  const double af1 = (fabs(lam1dt) < lim) ? coef1 : DDIV(coef1 * (elam1dt - 1.0), lam1dt);
+  const double af2 = (fabs(lam2dt) < lim) ? coef2 : DDIV(coef2 * (elam2dt - 1.0), lam2dt);
+  const double af3 = (fabs(lam3dt) < lim) ? coef3 : DDIV(coef3 * (elam3dt - 1.0), lam3dt);
   ion.h_av1 = rx + af1 + eigv2x * af2 + eigv3x * af3;
   ion.he_av1 = ry + eigv2y * af2 + eigv3y * af3;
   ion.he_av2 = rz + af2 + af3;
@@ -225,7 +300,7 @@ __device__ __forceinline__ int thermal(double dt, double& end_temper, double& av
   if (end_temper > minitemp) {
     const double* __restrict__ ct = d_run.cool;
     const double ne_av = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
-    const double kn_av = k_B * (n + ne_av);
+    const double rkn_av = fast_rcp(k_B * (n + ne_av));
     double cumulative_time = 0.0;
     avg_temper = 0.0;
     const double initial_temp = end_temper;
@@ -235,12 +310,12 @@ __device__ __forceinline__ int thermal(double dt, double& end_temper, double& av
       const double cooling =
           coolin(n, ne, ion.h_av0, ion.h_av1, ion.he_av0, ion.he_av1, ion.he_av2, end_temper, ct) + cosmo_cool_rate;
       const double thermal_rate = fmax(1e-50, fabs(cooling - heating));
-      const double thermal_timescale = internal_energy / fabs(thermal_rate);
+      const double thermal_timescale = fdiv(internal_energy, thermal_rate);
       const double dt_thermal = relative_denergy * thermal_timescale;
       const double dt_ODE = fmin(dt_thermal, dt - cumulative_time);
       internal_energy = internal_energy + dt_ODE * (heating - cooling);
       avg_temper = avg_temper + FL(0.5f) * end_temper * dt_ODE;
-      end_temper = (internal_energy * gamma1) / kn_av;
+      end_temper = (internal_energy * gamma1) * rkn_av;
       avg_temper = avg_temper + FL(0.5f) * end_temper * dt_ODE;
       if (end_temper < minitemp) {
         internal_energy = (n + ne_av) * k_B * minitemp;  // thermal.f90:141 (no /gamma1, as in the reference)
@@ -279,14 +354,14 @@ __device__ __forceinline__ int do_chemistry(double dt, double n, Ion& ion, doubl
     const double oldhav = ion.h_av0, oldhe0av = ion.he_av0, oldhe1av = ion.he_av1;
     doric(dt, de, ion, phiHI, phiHeI, phiHeII, fr, rc, clumping);
     // evolve_point.F90:588-595: h_av(1) and he_av(2) keep their pass-2 values
-    ion.h0 = (ion.h0 + ionh0old) / 2.0;
-    ion.h1 = (ion.h1 + ionh1old) / 2.0;
-    ion.he0 = (ion.he0 + ionhe0old) / 2.0;
-    ion.he1 = (ion.he1 + ionhe1old) / 2.0;
-    ion.he2 = (ion.he2 + ionhe2old) / 2.0;
-    ion.h_av0 = (ion.h_av0 + oldhav) / 2.0;
-    ion.he_av0 = (ion.he_av0 + oldhe0av) / 2.0;
-    ion.he_av1 = (ion.he_av1 + oldhe1av) / 2.0;
+    ion.h0 = (ion.h0 + ionh0old) * 0.5;
+    ion.h1 = (ion.h1 + ionh1old) * 0.5;
+    ion.he0 = (ion.he0 + ionhe0old) * 0.5;
+    ion.he1 = (ion.he1 + ionhe1old) * 0.5;
+    ion.he2 = (ion.he2 + ionhe2old) * 0.5;
+    ion.h_av0 = (ion.h_av0 + oldhav) * 0.5;
+    ion.he_av0 = (ion.he_av0 + oldhe0av) * 0.5;
+    ion.he_av1 = (ion.he_av1 + oldhe1av) * 0.5;
     de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
     temper1 = temper0;
     if (!iso) thermal(dt, temper1, avg_temper, de, n, ion, heat);
