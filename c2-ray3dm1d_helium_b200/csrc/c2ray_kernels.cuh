@@ -74,8 +74,11 @@ __device__ __forceinline__ void shell_decode(int c, int r, int& di, int& dj, int
 }
 
 __device__ __forceinline__ int wrap0(int p1, int n) {  // 1-based unwrapped -> 0-based periodic (modulo(p-1,n))
-  int m = (p1 - 1) % n;
-  return m < 0 ? m + n : m;
+  // traced offsets reach at most n/2 cells from a mesh position, so one conditional wrap is the whole modulo
+  int m = p1 - 1;
+  m += (m < 0) ? n : 0;
+  m -= (m >= n) ? n : 0;
+  return m;
 }
 
 __global__ void k_slots_init(Slot* slots, int nslots, const int* __restrict__ src_ids, const int* __restrict__ srcpos,
@@ -255,21 +258,21 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
       num = 0.0; den = 0.0;
 #pragma unroll
       for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf_fast(cH[q], sigma_HI_at_ion_freq); num += cH[q] * w; den += w; }
-      cin_H = num / den;
+      cin_H = fdiv(num, den);
       num = 0.0; den = 0.0;
 #pragma unroll
       for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf_fast(cHe0[q], sigma_HeI_at_ion_freq); num += cHe0[q] * w; den += w; }
-      cin_He0 = num / den;
+      cin_He0 = fdiv(num, den);
       num = 0.0; den = 0.0;
 #pragma unroll
       for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf_fast(cHe1[q], sigma_HeII_at_ion_freq); num += cHe1[q] * w; den += w; }
-      cin_He1 = num / den;
+      cin_He1 = fdiv(num, den);
       const int wa = abs(dw), ua = abs(du), va = abs(dv);
       if (wa == 1 && (ua == 1 || va == 1)) {  // :174-184
         const double f = (ua == 1 && va == 1) ? sqrt3 : sqrt2;
         cin_H = f * cin_H; cin_He0 = f * cin_He0; cin_He1 = f * cin_He1;
       }
-      path = sqrt((fu * fu + fv * fv) / (fw * fw) + 1.0);  // :194
+      path = sqrt(fdiv(fu * fu + fv * fv, fw * fw) + 1.0);  // :194
       path = path * d_run.dr[0];                            // evolve_point.F90:158
       const double xs = d_run.dr[0] * ddi, ys = d_run.dr[1] * ddj, zs = d_run.dr[2] * ddk;
       const double dist2 = xs * xs + ys * ys + zs * zs;
@@ -284,17 +287,31 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     PhotOut phi = {0, 0, 0, 0, 0, 0};
     if (cin_H < max_coldensh) {  // :250-270
       phi = photoion_rates<ISO, MULTI>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, vol_ph, S.nflux, yR);
-      phi.photo_HI = phi.photo_HI / (h_av0 * ndens_p * (1.0 - abu_he));
-      phi.photo_HeI = phi.photo_HeI / (he_av0 * ndens_p * abu_he);
-      phi.photo_HeII = phi.photo_HeII / (he_av1 * ndens_p * abu_he);
+      phi.photo_HI = fdiv(phi.photo_HI, h_av0 * ndens_p * (1.0 - abu_he));
+      phi.photo_HeI = fdiv(phi.photo_HeI, he_av0 * ndens_p * abu_he);
+      phi.photo_HeII = fdiv(phi.photo_HeII, he_av1 * ndens_p * abu_he);
     }
     atomicAdd(G.rates + p, phi.photo_HI);                // :299-306
     atomicAdd(G.rates + G.N3 + p, phi.photo_HeI);
     atomicAdd(G.rates + 2 * G.N3 + p, phi.photo_HeII);
     if (!iso) atomicAdd(G.rates + 3 * G.N3 + p, phi.heat);
-    // :310-314 photon loss over the current sub-box boundary
-    if (di == -S.lo[0] || dj == -S.lo[1] || dk == -S.lo[2] || di == S.hi[0] || dj == S.hi[1] || dk == S.hi[2])
-      atomicAdd(&S.loss, phi.photo_out * d_run.vol / vol_ph);
+    // :310-314 photon loss over the current sub-box boundary.  On the outermost shells every cell is a loss cell of
+    // one of a handful of sources: a full warp working on one source sums its contributions by shuffles first, so the
+    // per-source counter sees one atomic per warp instead of 32.
+    const bool is_loss = di == -S.lo[0] || dj == -S.lo[1] || dk == -S.lo[2] || di == S.hi[0] || dj == S.hi[1] || dk == S.hi[2];
+    const unsigned am = __activemask();
+    if (__any_sync(am, is_loss)) {
+      double lv = is_loss ? fdiv(phi.photo_out * d_run.vol, vol_ph) : 0.0;
+      int same = 0;
+      if (am == 0xffffffffu) __match_all_sync(am, sid, &same);
+      if (same) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&S.loss, lv);
+      } else if (is_loss) {
+        atomicAdd(&S.loss, lv);
+      }
+    }
     done++;
   }
   __syncwarp();
@@ -582,8 +599,8 @@ __global__ void k_cinterp_batch(int n, const int* __restrict__ pos, int i0, int 
   const double sg[3] = {sigma_HI_at_ion_freq, sigma_HeI_at_ion_freq, sigma_HeII_at_ion_freq};
   for (int s = 0; s < 3; s++) {
     double num = 0.0, den = 0.0;
-    for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf(cc[s][q], sg[s]); num += cc[s][q] * w; den += w; }
-    r3[s] = num / den;
+    for (int q = 0; q < 4; q++) { const double w = sw[q] * weightf_fast(cc[s][q], sg[s]); num += cc[s][q] * w; den += w; }
+    r3[s] = fdiv(num, den);
   }
   const int wa = abs(dw), ua = abs(du), va = abs(dv);
   if (wa == 1 && (ua == 1 || va == 1)) {
@@ -591,7 +608,7 @@ __global__ void k_cinterp_batch(int n, const int* __restrict__ pos, int i0, int 
     r3[0] *= f; r3[1] *= f; r3[2] *= f;
   }
   out4[4 * t] = r3[0]; out4[4 * t + 1] = r3[1]; out4[4 * t + 2] = r3[2];
-  out4[4 * t + 3] = sqrt((fu * fu + fv * fv) / (fw * fw) + 1.0);
+  out4[4 * t + 3] = sqrt(fdiv(fu * fu + fv * fv, fw * fw) + 1.0);
 }
 
 // FP64 FMA throughput probe
