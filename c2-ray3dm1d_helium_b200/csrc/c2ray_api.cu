@@ -108,6 +108,9 @@ struct c2ray_ctx {
   ChemTotals* d_chem = nullptr;
   double* d_sums = nullptr;
   double* d_secion = nullptr;
+  unsigned long long* d_next_cell = nullptr;
+  int chem_mode = -1;      // -1 auto, 0 one cell per thread, 1 queue-driven (env C2RAY_CHEM_QUEUE overrides)
+  double last_nsub_per_cell = 0.0;  // thermal sub-steps per cell of the previous global pass
   int* d_nit = nullptr;
   // multi-GPU
   int rank = 0, npr = 1;
@@ -325,8 +328,24 @@ int global_pass_launch(c2ray_ctx* c, double dt, int* d_nit) {
   if (!c->par.isothermal && !c->have_cool) return fail(C2RAY_ERR_STATE, "cooling tables not set (c2ray_b200_set_cooling_tables)");
   CK(cudaMemsetAsync(c->d_chem, 0, sizeof(ChemTotals), c->stream));
   ChemPtrs P{c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->temp, c->rates, c->N3};
-  const unsigned blocks = (unsigned)((c->N3 + 127) / 128);
-  LAUNCH(c, k_global_pass, blocks, 128, P, dt, c->d_chem, d_nit);
+  // auto: the queue-driven kernel pays off once cells need many thermal sub-steps (divergence); measured break-even
+  // between 10 and 40 sub-steps per cell (config 2: ~10, simple kernel faster; config 5: 42, queue 2x faster)
+  const bool use_queue = c->chem_mode == 1 || (c->chem_mode < 0 && c->last_nsub_per_cell > 20.0);
+  if (use_queue) {
+    // queue-driven: a persistent grid of lanes drawing cells from a counter (k_global_pass_q)
+    CK(cudaMemsetAsync(c->d_next_cell, 0, sizeof(unsigned long long), c->stream));
+    static int per_sm = 0, n_sm = 0;
+    if (!per_sm) {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_global_pass_q, 128, 0));
+      CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
+      per_sm = std::max(per_sm, 1);
+    }
+    const unsigned blocks = (unsigned)std::min<size_t>((c->N3 + 127) / 128, (size_t)n_sm * per_sm);
+    LAUNCH(c, k_global_pass_q, blocks, 128, P, dt, c->d_chem, d_nit, c->d_next_cell);
+  } else {
+    const unsigned blocks = (unsigned)((c->N3 + 127) / 128);
+    LAUNCH(c, k_global_pass, blocks, 128, P, dt, c->d_chem, d_nit);
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -402,6 +421,8 @@ int c2ray_b200_init(const c2ray_params* params, const int32_t mesh[3], int32_t d
   CK(cudaMalloc(&c->d_tot, sizeof(SweepTotals)));
   CK(cudaMalloc(&c->d_chem, sizeof(ChemTotals)));
   CK(cudaMalloc(&c->d_sums, 5 * sizeof(double)));
+  CK(cudaMalloc(&c->d_next_cell, sizeof(unsigned long long)));
+  if (const char* e = getenv("C2RAY_CHEM_QUEUE")) c->chem_mode = atoi(e);
   CK(cudaMalloc(&c->d_cool, 5 * TEMPPOINTS * sizeof(double)));
   CK(cudaMalloc(&c->d_tb, sizeof(TableBuild)));
   int rc = upload_band_const(c);
@@ -418,7 +439,7 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   void* ptrs[] = {c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->rates, c->temp, c->snap_xh,
                   c->snap_xhe, c->snap_temp, c->d_srcpos, c->d_nf, c->d_nfpl, c->d_nfqpl, c->d_srcids, c->d_tb, c->d_cool,
-                  c->d_slots, c->d_active, c->d_tot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion};
+                  c->d_slots, c->d_active, c->d_tot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
   for (int s = 0; s < 3; s++) if (c->packed[s]) cudaFree(c->packed[s]);
@@ -774,6 +795,7 @@ int c2ray_b200_global_pass(c2ray_ctx* c, double dt, int32_t* conv_flag, int32_t*
   CK(cudaMemcpyAsync(&t, c->d_chem, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
   if (nit_out) CK(cudaMemcpyAsync(nit_out, c->d_nit, c->N3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  c->last_nsub_per_cell = (double)t.nsub_total / (double)c->N3;
   if (conv_flag) *conv_flag = t.conv_flag;
   return C2RAY_OK;
 }
@@ -823,6 +845,7 @@ int c2ray_b200_evolve3d(c2ray_ctx* c, double /*time*/, double dt, int32_t restar
     CK(cudaEventRecord(c->ev[0], c->stream));  // iteration end
     CK(cudaStreamSynchronize(c->stream));
     conv_flag = cht.conv_flag;
+    c->last_nsub_per_cell = (double)cht.nsub_total / (double)c->N3;
     if (niter <= C2RAY_MAX_ITER_HIST) S.conv_hist[niter - 1] = conv_flag;
     S.rt_updates += (int64_t)swt.updates;
     S.chem_cells += (int64_t)c->N3;
@@ -984,6 +1007,7 @@ int c2ray_b200_bench_global_pass(c2ray_ctx* c, double dt, int32_t reps, double* 
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
     total += ms;
+    c->last_nsub_per_cell = (double)t.nsub_total / (double)c->N3;
   }
   if (ms_per_pass) *ms_per_pass = total / reps;
   if (conv_flag) *conv_flag = t.conv_flag;

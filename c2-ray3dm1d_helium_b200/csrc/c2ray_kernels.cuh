@@ -338,6 +338,7 @@ struct ChemTotals {
   int conv_flag;
   int nit_max;
   unsigned long long nit_total;
+  unsigned long long nsub_total;  // explicit thermal sub-steps taken (drives the choice of global-pass kernel)
 };
 
 __global__ void __launch_bounds__(128)
@@ -345,7 +346,7 @@ k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out)
   const size_t N3 = P.N3;
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool iso = d_run.isothermal != 0;
-  int vote = 0, nit = 0;
+  int vote = 0, nit = 0, nsub = 0;
   if (p < N3) {
     Ion ion;
     // evolve_point.F90:368-378.  Only the live members are loaded: ion%h(1), ion%he(2) are
@@ -371,7 +372,7 @@ k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out)
     RecCol rc;
     if (iso) ini_rec_colion_factors(d_run.temper_val, rc);  // mat_ini_test.F90:168
     double avg_temper = temp_av_old, temper1;
-    nit = do_chemistry(dt, n, ion, phiHI, phiHeI, phiHeII, heat, temper_old, avg_temper, temper1, rc);
+    nit = do_chemistry(dt, n, ion, phiHI, phiHeI, phiHeII, heat, temper_old, avg_temper, temper1, rc, &nsub);
     double temp_av_new = temp_av_old;
     if (!iso) {  // set_temperature_point: stored as real(si), read back as such (:404)
       const float t0 = (float)temper1, t1 = (float)avg_temper;
@@ -394,9 +395,135 @@ k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out)
   const unsigned int v = __reduce_add_sync(0xffffffffu, (unsigned)vote);
   const unsigned int ns = __reduce_add_sync(0xffffffffu, (unsigned)nit);
   const unsigned int nm = __reduce_max_sync(0xffffffffu, (unsigned)nit);
+  const unsigned int nsb = __reduce_add_sync(0xffffffffu, (unsigned)nsub);
   if ((threadIdx.x & 31) == 0) {
     if (v) atomicAdd(&tot->conv_flag, (int)v);
     atomicAdd(&tot->nit_total, (unsigned long long)ns);
+    if (nsb) atomicAdd(&tot->nsub_total, (unsigned long long)nsb);
+    atomicMax(&tot->nit_max, (int)nm);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (c') queue-driven global pass.  do_chemistry's cost per cell varies by three orders of magnitude (1..401 outer
+// iterations x 1..10001 explicit thermal sub-steps), so with one cell per thread a warp idles behind its slowest lane
+// (measured on the BASELINE config-5 inputs: mean 42 sub-steps per cell, mean of the per-warp maximum 272).  Here every
+// lane is a small state machine -- IONIZE (coefficients + doric x2) -> THERMAL (a bounded burst of sub-steps) ->
+// TEST (convergence; store or loop) -- and a lane that finishes its cell immediately draws the next cell index from a
+// global counter (one atomic per warp refill).  The arithmetic per cell is exactly that of do_chemistry.
+// ------------------------------------------------------------------------------------------------
+constexpr int CHEM_BURST = 32;  // thermal sub-steps per state-machine turn (8: 36 ms, 32: 30 ms on config 5 at 256^3)
+
+__global__ void __launch_bounds__(128, 3)
+k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out, unsigned long long* next_cell) {
+  const size_t N3 = P.N3;
+  const bool iso = d_run.isothermal != 0;
+  const unsigned lane = threadIdx.x & 31;
+  enum { IDLE = 0, IONIZE = 1, THERMAL = 2, TEST = 3 };
+  int phase = IDLE;
+  bool exhausted = false;
+  long long p = -1;
+  Ion ion;
+  RecCol rc;
+  ThermState TS;
+  ChemIter it;
+  double n = 0, phiHI = 0, phiHeI = 0, phiHeII = 0, heat = 0, de = 0;
+  double temper0 = 0, temper1 = 0, avg_temper = 0, temp_av_old = 0, yh0_old = 0, yhe0_old = 0, yhe2_old = 0;
+  int nit = 0, votes = 0, nit_sum = 0, nit_max = 0, nsub = 0;
+  if (iso) ini_rec_colion_factors(d_run.temper_val, rc);  // mat_ini_test.F90:168
+
+  for (;;) {
+    // ---- refill idle lanes ----------------------------------------------------------------------------------
+    const unsigned want = __ballot_sync(0xffffffffu, phase == IDLE && !exhausted);
+    if (want) {
+      unsigned long long base = 0;
+      if (lane == (unsigned)(__ffs(want) - 1)) base = atomicAdd(next_cell, (unsigned long long)__popc(want));
+      base = __shfl_sync(0xffffffffu, base, __ffs(want) - 1);
+      if (phase == IDLE && !exhausted) {
+        const unsigned long long idx = base + __popc(want & ((1u << lane) - 1));
+        if (idx >= N3) {
+          exhausted = true;
+        } else {
+          p = (long long)idx;
+          // evolve_point.F90:368-390, live members only (see k_global_pass)
+          ion.h0 = fmax(epsilon, P.xh_int[p]);
+          ion.he0 = fmax(epsilon, P.xhe_int[p]);
+          ion.he1 = fmax(epsilon, P.xhe_int[p + N3]);
+          ion.h1 = 0.0; ion.he2 = 0.0; ion.h_old0 = 0.0; ion.he_old0 = 0.0;
+          ion.h_old1 = fmax(epsilon, P.xh[p + N3]);
+          ion.he_old1 = fmax(epsilon, P.xhe[p + N3]);
+          ion.he_old2 = fmax(epsilon, P.xhe[p + 2 * N3]);
+          yh0_old = P.xh_av[p]; yhe0_old = P.xhe_av[p]; yhe2_old = P.xhe_av[p + 2 * N3];
+          ion.h_av0 = fmax(epsilon, yh0_old); ion.h_av1 = fmax(epsilon, P.xh_av[p + N3]);
+          ion.he_av0 = fmax(epsilon, yhe0_old); ion.he_av1 = fmax(epsilon, P.xhe_av[p + N3]);
+          ion.he_av2 = fmax(epsilon, yhe2_old);
+          n = P.ndens[p];
+          if (iso) { temp_av_old = d_run.temper_val; temper0 = d_run.temper_val; }
+          else { temp_av_old = (double)P.temp[p + N3]; temper0 = (double)P.temp[p + 2 * N3]; }
+          phiHI = P.rates[p]; phiHeI = P.rates[N3 + p]; phiHeII = P.rates[2 * N3 + p];
+          heat = iso ? 0.0 : P.rates[3 * N3 + p];
+          avg_temper = temp_av_old; temper1 = temper0; nit = 0;
+          phase = IONIZE;
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, phase == IDLE)) break;  // every lane idle and the queue empty
+
+    // ---- IONIZE: one do_chemistry iteration up to the thermal call (evolve_point.F90:488-600) ---------------------
+    if (phase == IONIZE) {
+      nit++;
+      de = chem_ionization(dt, n, ion, phiHI, phiHeI, phiHeII, avg_temper, temper1, rc, it);
+      temper1 = temper0;
+      if (iso) {
+        phase = TEST;
+      } else {
+        thermal_begin(TS, temper1, n, ion);
+        phase = TS.active ? THERMAL : TEST;
+      }
+    }
+    // ---- THERMAL: a burst of explicit sub-steps (thermal.f90:98-157) -----------------------------------------------
+    if (phase == THERMAL) {
+      bool done = false;
+#pragma unroll 1
+      for (int k = 0; k < CHEM_BURST && !done; k++) { done = thermal_substep(TS, dt, de, n, ion, heat); nsub++; }
+      if (done) phase = TEST;
+    }
+    // ---- TEST: finish thermal, convergence test, store (evolve_point.F90:607-644, :397-435) --------------------------
+    if (phase == TEST) {
+      if (!iso) thermal_end(TS, dt, n, ion, temper1, avg_temper);
+      if (chem_converged(ion, it, temper1) || nit > 400) {
+        double temp_av_new = temp_av_old;
+        if (!iso) {
+          const float t0 = (float)temper1, t1 = (float)avg_temper;
+          P.temp[p] = t0; P.temp[p + N3] = t1;
+          temp_av_new = (double)t1;
+        }
+        const double mfc = minimum_fractional_change, mfa = minimum_fraction_of_atoms;
+        if ((fabs(ion.h_av0 - yh0_old) > mfc && fabs((ion.h_av0 - yh0_old) / ion.h_av0) > mfc && ion.h_av0 > mfa) ||
+            (fabs(ion.he_av0 - yhe0_old) > mfc && fabs((ion.he_av0 - yhe0_old) / ion.he_av0) > mfc && ion.he_av0 > mfa) ||
+            (fabs(ion.he_av2 - yhe2_old) > mfc && fabs((ion.he_av2 - yhe2_old) / ion.he_av2) > mfc && ion.he_av2 > mfa) ||
+            ((fabs((temp_av_old - temp_av_new) / temp_av_new) > 1.0e-1) && (fabs(temp_av_new - temp_av_old) > 100.0)))
+          votes++;
+        P.xh_int[p] = ion.h0; P.xh_int[p + N3] = ion.h1;
+        P.xh_av[p] = ion.h_av0; P.xh_av[p + N3] = ion.h_av1;
+        P.xhe_int[p] = ion.he0; P.xhe_int[p + N3] = ion.he1; P.xhe_int[p + 2 * N3] = ion.he2;
+        P.xhe_av[p] = ion.he_av0; P.xhe_av[p + N3] = ion.he_av1; P.xhe_av[p + 2 * N3] = ion.he_av2;
+        if (nit_out) nit_out[p] = nit;
+        nit_sum += nit; nit_max = max(nit_max, nit);
+        phase = IDLE;
+      } else {
+        phase = IONIZE;
+      }
+    }
+  }
+  const unsigned int v = __reduce_add_sync(0xffffffffu, (unsigned)votes);
+  const unsigned int ns = __reduce_add_sync(0xffffffffu, (unsigned)nit_sum);
+  const unsigned int nm = __reduce_max_sync(0xffffffffu, (unsigned)nit_max);
+  const unsigned int nsb = __reduce_add_sync(0xffffffffu, (unsigned)nsub);
+  if (lane == 0) {
+    if (v) atomicAdd(&tot->conv_flag, (int)v);
+    atomicAdd(&tot->nit_total, (unsigned long long)ns);
+    if (nsb) atomicAdd(&tot->nsub_total, (unsigned long long)nsb);
     atomicMax(&tot->nit_max, (int)nm);
   }
 }

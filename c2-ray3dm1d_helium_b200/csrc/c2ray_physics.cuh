@@ -290,87 +290,128 @@ __device__ __forceinline__ void doric(double dt, double rhe, Ion& ion, double ph
   }
 }
 
-// thermal.f90:22-174 ; returns the number of sub-steps
-__device__ __forceinline__ int thermal(double dt, double& end_temper, double& avg_temper, double ne, double n,
-                                       const Ion& ion, double heating) {
-  double internal_energy = (n + electrondens(n, ion.h_old1, ion.he_old1, ion.he_old2)) * k_B * end_temper / gamma1;
-  const double cosmo_cool_rate =
-      d_run.cosmological ? internal_energy * FL(2.0f) / d_run.zp1 * d_run.dzdt : 0.0;  // cosmology.f90:232
-  int i_heating = 0;
-  if (end_temper > minitemp) {
-    const double* __restrict__ ct = d_run.cool;
-    const double ne_av = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
-    const double rkn_av = fast_rcp(k_B * (n + ne_av));
-    double cumulative_time = 0.0;
-    avg_temper = 0.0;
-    const double initial_temp = end_temper;
-    const double tol = FL(1e-6f) * dt;
-    for (;;) {
-      i_heating++;
-      const double cooling =
-          coolin(n, ne, ion.h_av0, ion.h_av1, ion.he_av0, ion.he_av1, ion.he_av2, end_temper, ct) + cosmo_cool_rate;
-      const double thermal_rate = fmax(1e-50, fabs(cooling - heating));
-      const double thermal_timescale = fdiv(internal_energy, thermal_rate);
-      const double dt_thermal = relative_denergy * thermal_timescale;
-      const double dt_ODE = fmin(dt_thermal, dt - cumulative_time);
-      internal_energy = internal_energy + dt_ODE * (heating - cooling);
-      avg_temper = avg_temper + FL(0.5f) * end_temper * dt_ODE;
-      end_temper = (internal_energy * gamma1) * rkn_av;
-      avg_temper = avg_temper + FL(0.5f) * end_temper * dt_ODE;
-      if (end_temper < minitemp) {
-        internal_energy = (n + ne_av) * k_B * minitemp;  // thermal.f90:141 (no /gamma1, as in the reference)
-        end_temper = minitemp;
-      }
-      cumulative_time = cumulative_time + dt_ODE;
-      if (cumulative_time >= dt || fabs(cumulative_time - dt) < tol) break;
-      if (i_heating > 10000) break;
-    }
-    avg_temper = (dt > 0.0) ? avg_temper / dt : initial_temp;
-    end_temper = (internal_energy * gamma1) / (k_B * (n + electrondens(n, ion.h1, ion.he1, ion.he2)));
-  }
-  return i_heating;
+// thermal.f90:22-174, split into begin / sub-step / end so that the queue-driven global pass (k_global_pass_q) can
+// suspend a cell between sub-steps; thermal() below composes the three and is what the batch hook runs.
+struct ThermState {
+  double internal_energy, end_temper, avg_acc, cumulative_time, cosmo_cool_rate, ne_av, rkn_av, initial_temp;
+  int i_heating;
+  bool active;   // end_temper > minitemp at entry (thermal.f90:83)
+};
+
+__device__ __forceinline__ void thermal_begin(ThermState& S, double end_temper, double n, const Ion& ion) {
+  S.internal_energy = (n + electrondens(n, ion.h_old1, ion.he_old1, ion.he_old2)) * k_B * end_temper / gamma1;  // :68
+  S.cosmo_cool_rate = d_run.cosmological ? S.internal_energy * FL(2.0f) / d_run.zp1 * d_run.dzdt : 0.0;  // cosmology.f90:232
+  S.i_heating = 0;
+  S.end_temper = end_temper;
+  S.initial_temp = end_temper;
+  S.active = end_temper > minitemp;
+  S.ne_av = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
+  S.rkn_av = fast_rcp(k_B * (n + S.ne_av));
+  S.cumulative_time = 0.0;
+  S.avg_acc = 0.0;
 }
 
-// evolve_point.F90:444-646 do_chemistry (local=.false.); temper1 in: T_old (grid(..,2)); avg_temper in: grid(..,1)
-__device__ __forceinline__ int do_chemistry(double dt, double n, Ion& ion, double phiHI, double phiHeI, double phiHeII,
-                                            double heat, double temper_old, double& avg_temper, double& temper1_out,
-                                            RecCol& rc) {
+// one explicit sub-step (:98-157); returns true when the loop of the reference would exit
+__device__ __forceinline__ bool thermal_substep(ThermState& S, double dt, double ne, double n, const Ion& ion,
+                                                double heating) {
+  S.i_heating++;
+  const double cooling =
+      coolin(n, ne, ion.h_av0, ion.h_av1, ion.he_av0, ion.he_av1, ion.he_av2, S.end_temper, d_run.cool) + S.cosmo_cool_rate;
+  const double thermal_rate = fmax(1e-50, fabs(cooling - heating));
+  const double thermal_timescale = fdiv(S.internal_energy, thermal_rate);
+  const double dt_thermal = relative_denergy * thermal_timescale;
+  const double dt_ODE = fmin(dt_thermal, dt - S.cumulative_time);
+  S.internal_energy = S.internal_energy + dt_ODE * (heating - cooling);
+  S.avg_acc = S.avg_acc + FL(0.5f) * S.end_temper * dt_ODE;
+  S.end_temper = (S.internal_energy * gamma1) * S.rkn_av;
+  S.avg_acc = S.avg_acc + FL(0.5f) * S.end_temper * dt_ODE;
+  if (S.end_temper < minitemp) {
+    S.internal_energy = (n + S.ne_av) * k_B * minitemp;  // thermal.f90:141 (no /gamma1, as in the reference)
+    S.end_temper = minitemp;
+  }
+  S.cumulative_time = S.cumulative_time + dt_ODE;
+  if (S.cumulative_time >= dt || fabs(S.cumulative_time - dt) < FL(1e-6f) * dt) return true;
+  return S.i_heating > 10000;
+}
+
+// :159-172 ; avg_temper is left untouched when the cell was at or below minitemp (quirk q3)
+__device__ __forceinline__ void thermal_end(const ThermState& S, double dt, double n, const Ion& ion, double& end_temper,
+                                            double& avg_temper) {
+  if (!S.active) return;
+  avg_temper = (dt > 0.0) ? S.avg_acc / dt : S.initial_temp;
+  end_temper = (S.internal_energy * gamma1) / (k_B * (n + electrondens(n, ion.h1, ion.he1, ion.he2)));
+}
+
+__device__ __forceinline__ int thermal(double dt, double& end_temper, double& avg_temper, double ne, double n,
+                                       const Ion& ion, double heating) {
+  ThermState S;
+  thermal_begin(S, end_temper, n, ion);
+  if (S.active)
+    while (!thermal_substep(S, dt, ne, n, ion, heating)) {}
+  thermal_end(S, dt, n, ion, end_temper, avg_temper);
+  return S.i_heating;
+}
+
+// evolve_point.F90:444-646 do_chemistry (local=.false.), split at the thermal call.
+struct ChemIter {  // values the convergence test of one iteration needs (:488-496)
+  double yh0_av_old, yhe0_av_old, yhe2_av_old, temper2;
+};
+
+// :488-597: coefficients at avg_temper, doric twice with the partial averaging; returns the electron density for thermal
+__device__ __forceinline__ double chem_ionization(double dt, double n, Ion& ion, double phiHI, double phiHeI,
+                                                  double phiHeII, double avg_temper, double temper1, RecCol& rc,
+                                                  ChemIter& it) {
   const bool iso = d_run.isothermal != 0;
   const double clumping = d_run.clumping;
+  it.temper2 = temper1;
+  it.yh0_av_old = ion.h_av0; it.yhe0_av_old = ion.he_av0; it.yhe2_av_old = ion.he_av2;
+  double de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
+  if (!iso) ini_rec_colion_factors(avg_temper, rc);
+  DoricFrac fr = prepare_doric_factors(n, ion.h0, ion.he0, ion.he1);
+  doric(dt, de, ion, phiHI, phiHeI, phiHeII, fr, rc, clumping);
+  de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
+  fr = prepare_doric_factors(n, ion.h0, ion.he0, ion.he1);
+  const double ionh0old = ion.h0, ionh1old = ion.h1, ionhe0old = ion.he0, ionhe1old = ion.he1, ionhe2old = ion.he2;
+  const double oldhav = ion.h_av0, oldhe0av = ion.he_av0, oldhe1av = ion.he_av1;
+  doric(dt, de, ion, phiHI, phiHeI, phiHeII, fr, rc, clumping);
+  // evolve_point.F90:588-595: h_av(1) and he_av(2) keep their pass-2 values
+  ion.h0 = (ion.h0 + ionh0old) * 0.5;
+  ion.h1 = (ion.h1 + ionh1old) * 0.5;
+  ion.he0 = (ion.he0 + ionhe0old) * 0.5;
+  ion.he1 = (ion.he1 + ionhe1old) * 0.5;
+  ion.he2 = (ion.he2 + ionhe2old) * 0.5;
+  ion.h_av0 = (ion.h_av0 + oldhav) * 0.5;
+  ion.he_av0 = (ion.he_av0 + oldhe0av) * 0.5;
+  ion.he_av1 = (ion.he_av1 + oldhe1av) * 0.5;
+  return electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
+}
+
+// :607-628
+__device__ __forceinline__ bool chem_converged(const Ion& ion, const ChemIter& it, double temper1) {
+  return (fabs((ion.h_av0 - it.yh0_av_old) / ion.h_av0) < minimum_fractional_change || ion.h_av0 < minimum_fraction_of_atoms) &&
+         (fabs((ion.he_av0 - it.yhe0_av_old) / ion.he_av0) < minimum_fractional_change || ion.he_av0 < minimum_fraction_of_atoms) &&
+         (fabs((ion.he_av2 - it.yhe2_av_old) / ion.he_av2) < minimum_fractional_change || ion.he_av2 < minimum_fraction_of_atoms) &&
+         (fabs((temper1 - it.temper2) / temper1) < minimum_fractional_change);
+}
+
+// temper_old: T at the start of the step (grid(..,2)); avg_temper in: grid(..,1)
+__device__ __forceinline__ int do_chemistry(double dt, double n, Ion& ion, double phiHI, double phiHeI, double phiHeII,
+                                            double heat, double temper_old, double& avg_temper, double& temper1_out,
+                                            RecCol& rc, int* nsub_total = nullptr) {
+  const bool iso = d_run.isothermal != 0;
   double temper1 = temper_old;
   const double temper0 = temper1;
   int nit = 0;
   for (;;) {
     nit++;
-    const double temper2 = temper1;
-    const double yh0_av_old = ion.h_av0, yhe0_av_old = ion.he_av0, yhe2_av_old = ion.he_av2;
-    double de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
-    if (!iso) ini_rec_colion_factors(avg_temper, rc);
-    DoricFrac fr = prepare_doric_factors(n, ion.h0, ion.he0, ion.he1);
-    doric(dt, de, ion, phiHI, phiHeI, phiHeII, fr, rc, clumping);
-    de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
-    fr = prepare_doric_factors(n, ion.h0, ion.he0, ion.he1);
-    const double ionh0old = ion.h0, ionh1old = ion.h1, ionhe0old = ion.he0, ionhe1old = ion.he1, ionhe2old = ion.he2;
-    const double oldhav = ion.h_av0, oldhe0av = ion.he_av0, oldhe1av = ion.he_av1;
-    doric(dt, de, ion, phiHI, phiHeI, phiHeII, fr, rc, clumping);
-    // evolve_point.F90:588-595: h_av(1) and he_av(2) keep their pass-2 values
-    ion.h0 = (ion.h0 + ionh0old) * 0.5;
-    ion.h1 = (ion.h1 + ionh1old) * 0.5;
-    ion.he0 = (ion.he0 + ionhe0old) * 0.5;
-    ion.he1 = (ion.he1 + ionhe1old) * 0.5;
-    ion.he2 = (ion.he2 + ionhe2old) * 0.5;
-    ion.h_av0 = (ion.h_av0 + oldhav) * 0.5;
-    ion.he_av0 = (ion.he_av0 + oldhe0av) * 0.5;
-    ion.he_av1 = (ion.he_av1 + oldhe1av) * 0.5;
-    de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
+    ChemIter it;
+    const double de = chem_ionization(dt, n, ion, phiHI, phiHeI, phiHeII, avg_temper, temper1, rc, it);
     temper1 = temper0;
-    if (!iso) thermal(dt, temper1, avg_temper, de, n, ion, heat);
-    const bool ok =
-        (fabs((ion.h_av0 - yh0_av_old) / ion.h_av0) < minimum_fractional_change || ion.h_av0 < minimum_fraction_of_atoms) &&
-        (fabs((ion.he_av0 - yhe0_av_old) / ion.he_av0) < minimum_fractional_change || ion.he_av0 < minimum_fraction_of_atoms) &&
-        (fabs((ion.he_av2 - yhe2_av_old) / ion.he_av2) < minimum_fractional_change || ion.he_av2 < minimum_fraction_of_atoms) &&
-        (fabs((temper1 - temper2) / temper1) < minimum_fractional_change);
-    if (ok) break;
+    if (!iso) {
+      const int ns = thermal(dt, temper1, avg_temper, de, n, ion, heat);
+      if (nsub_total) *nsub_total += ns;
+    }
+    if (chem_converged(ion, it, temper1)) break;
     if (nit > 400) break;
   }
   temper1_out = temper1;

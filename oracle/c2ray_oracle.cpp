@@ -1261,6 +1261,7 @@ void orc_thermal(double dt, double* end_temper, double* avg_temper, double ne, d
   thermal(dt, *end_temper, *avg_temper, ne, n, ion, phi, nsub);
 }
 
+static int* g_nsub_out = nullptr;
 // batch of independent cells through do_chemistry (evolve0D_global without the grid): in/out arrays of n cells.
 // ion15 [n][15], phi4 [n][4] (HI,HeI,HeII,heat), T3 [n][3] (inter, avg, old) doubles holding float values
 void orc_chemistry_batch(int n, double dt, const double* ndens, double* ion15, const double* phi4, double* T3, int* nit_out) {
@@ -1270,11 +1271,15 @@ void orc_chemistry_batch(int n, double dt, const double* ndens, double* ion15, c
     phi.heat = phi4[4 * c + 3];
     double avg = T3[3 * c + 1], t1;
     RecCol rc = G.rc;
-    nit_out[c] = do_chemistry(dt, ndens[c], ion, phi, T3[3 * c + 2], avg, t1, rc);
+    long nsub = 0;
+    nit_out[c] = do_chemistry(dt, ndens[c], ion, phi, T3[3 * c + 2], avg, t1, rc, &nsub);
+    if (g_nsub_out) g_nsub_out[c] = (int)nsub;
     T3[3 * c] = t1; T3[3 * c + 1] = avg;
     pack_ion(ion, ion15 + 15 * (size_t)c);
   }
 }
+// diagnostics: total thermal sub-steps per cell of the next orc_chemistry_batch call (NULL to switch off)
+void orc_set_nsub_out(int* p) { g_nsub_out = p; }
 
 // photoion_rates for n independent cells.  col6 [n][6] = in_HI,out_HI,in_HeI,out_HeI,in_HeII,out_HeII ;
 // out6 [n][6] = photo_cell_HI, HeI, HeII, heat, photo_in, photo_out
