@@ -1,0 +1,113 @@
+"""More GPU parity cases: non-cubic meshes (per-dimension reach and periodic wrap), deterministic mode, error paths of
+the C ABI on a live context, both global-pass kernels."""
+import os
+
+import numpy as np
+import pytest
+
+import c2ray_b200
+from c2ray_b200 import capi
+from oracle import oracle as O
+from common import oracle_setup, oracle_grid, relerr, frac_err
+
+pytestmark = pytest.mark.gpu
+synth = c2ray_b200.synth
+
+
+def noncubic_problem(mesh=(10, 14, 12), nsrc=2, sub=4, seed=3):
+    p = synth.make_problem(1, n=8)
+    rng = np.random.default_rng(seed)
+    m = np.array(mesh, dtype=np.int32)
+    shape = (mesh[2], mesh[1], mesh[0])
+    p["mesh"] = m
+    p["ndens"] = synth.mean_density(9.0) * np.exp(rng.standard_normal(shape) * 0.8)
+    xh = np.empty((2,) + shape); xhe = np.empty((3,) + shape)
+    xh[0] = 1.0 - 1e-20; xh[1] = 1e-20; xhe[0] = 1.0 - 2e-20; xhe[1] = 1e-20; xhe[2] = 1e-20
+    p["xh"], p["xhe"] = xh, xhe
+    p["temperature_grid"] = np.full((3,) + shape, 1.0e4, dtype=np.float32)
+    p["srcpos"] = np.stack([rng.integers(1, mesh[d] + 1, nsrc) for d in range(3)], axis=1).astype(np.int32)
+    p["NormFlux"] = np.full(nsrc, 3e6)
+    p["subboxsize"] = sub
+    return p
+
+
+@pytest.mark.parametrize("mesh,sub", [((10, 14, 12), 4), ((9, 8, 16), 3), ((16, 6, 7), 20)])
+def test_noncubic_mesh(mesh, sub):
+    p = noncubic_problem(mesh, sub=sub)
+    tables = oracle_setup(p)
+    g = oracle_grid(p)
+    g.set_work_state(p["xh"], p["xhe"], p["xh"], p["xhe"])
+    g.set_rates_to_zero()
+    upd_o, nbox_o, loss_o, sn_o = g.pass_all_sources()
+    ro = g.get_rates()
+    c = c2ray_b200.from_problem(p, tables=tables)
+    c.begin_step()
+    c.set_rates_to_zero()
+    assert c.pass_all_sources(1, p["dt"]) == upd_o
+    for a, b in zip(c.get_rates(), ro):
+        assert relerr(a, b, 1e-6 * np.abs(b).max() + 1e-300) < 1e-8
+        assert np.array_equal(a != 0, b != 0)  # identical cell coverage
+    assert [c.do_source(p["dt"], ns, 1)[0] for ns in range(1, len(p["NormFlux"]) + 1)] == list(nbox_o)
+    so = oracle_grid(p).evolve3d(p["dt"])
+    sg = c2ray_b200.from_problem(p, tables=tables).evolve3D(0.0, p["dt"], 0)
+    assert sg["niter"] == so["niter"] and list(sg["conv_hist"]) == list(so["conv_hist"])
+    c.close()
+
+
+def test_deterministic_mode_is_reproducible():
+    p = synth.make_problem(3, n=16, num_src=5)
+    tables = oracle_setup(p)
+    runs = []
+    for rep in range(2):
+        c = c2ray_b200.from_problem(p, tables=tables, deterministic=True)
+        c.begin_step(); c.set_rates_to_zero(); c.pass_all_sources(1, p["dt"])
+        runs.append(c.get_rates())
+        c.close()
+    for a, b in zip(*runs):
+        assert np.array_equal(a, b)  # one source at a time in source order: no atomic reordering
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_both_global_pass_kernels(mode, monkeypatch):
+    """C2RAY_CHEM_QUEUE=0: one cell per thread; =1: queue-driven lanes.  Same arithmetic, same integers."""
+    monkeypatch.setenv("C2RAY_CHEM_QUEUE", mode)
+    q = synth.make_chemistry_problem(20 ** 3, seed=9)
+    p = synth.make_problem(1, n=20)
+    p["ndens"] = q["ndens"].reshape(20, 20, 20)
+    tables = oracle_setup(p)
+    g = oracle_grid(p)
+    g.set_work_state(p["xh"], p["xhe"], p["xh"], p["xhe"])
+    rates = (q["phih"].reshape(20, 20, 20), q["phihe"].reshape(2, 20, 20, 20), q["phiheat"].reshape(20, 20, 20))
+    g.set_rates(*rates)
+    cf_o, nit_o = g.global_pass(q["dt"], want_nit=True)
+    c = c2ray_b200.from_problem(p, tables=tables)
+    c.begin_step()
+    c.set_rates(*rates)
+    cf, nit = c.global_pass(q["dt"], want_nit=True)
+    assert cf == cf_o and np.array_equal(nit.ravel(), nit_o)
+    for a, b in zip(c.get_work_state(), g.get_work_state()):
+        assert frac_err(a, b) < 1
+    assert relerr(c.get_state()[2][:2], g.get_state()[2][:2]) < 1.3e-7
+    c.close()
+
+
+def test_error_paths_on_a_live_context():
+    p = synth.make_problem(1, n=8)
+    par = c2ray_b200.C2RayParameters(H0=p["H0"])
+    c = c2ray_b200.C2Ray(p["mesh"], par)
+    c.set_geometry(p["dr"], p["vol"], p["zred"])
+    c.set_sources(p["srcpos"], p["NormFlux"])
+    c.set_state(p["ndens"], p["xh"], p["xhe"], p["temperature_grid"])
+    with pytest.raises(capi.C2RayError, match="no radiation tables"):
+        c.evolve3D(0.0, p["dt"], 0)
+    c.rad_ini(p["T_eff"], p["S_star"])
+    with pytest.raises(capi.C2RayError, match="cooling tables"):
+        c.evolve3D(0.0, p["dt"], 0)
+    c.setup_cool()
+    with pytest.raises(capi.C2RayError, match="restart"):
+        c.evolve3D(0.0, p["dt"], 1)
+    with pytest.raises(capi.C2RayError, match="bad source number"):
+        c.do_source(p["dt"], 5, 1)
+    st = c.evolve3D(0.0, p["dt"], 0)
+    assert st["niter"] >= 2
+    c.close()
