@@ -188,12 +188,16 @@ __device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, d
   bool act[3] = {true, false, false};
   int blo, bhi;
   double scale = 1.0;
+  unsigned long long bands = ~0ull;  // bit b-1: some active SED covers band b (BB and QPL ranges can leave a gap)
   if (MULTI) {
-    blo = NumFreqBnd + 1; bhi = 0;
+    blo = NumFreqBnd + 1; bhi = 0; bands = 0ull;
 #pragma unroll
     for (int s = 0; s < 3; s++) {
       act[s] = (d_run.sed[s].hi >= d_run.sed[s].lo) && (nflux[s] > 0.0);
-      if (act[s]) { blo = min(blo, d_run.sed[s].lo); bhi = max(bhi, d_run.sed[s].hi); }
+      if (act[s]) {
+        blo = min(blo, d_run.sed[s].lo); bhi = max(bhi, d_run.sed[s].hi);
+        bands |= (~0ull >> (64 - d_run.sed[s].hi)) & (~0ull << (d_run.sed[s].lo - 1));
+      }
     }
   } else {
     blo = d_run.sed[0].lo; bhi = d_run.sed[0].hi;
@@ -202,8 +206,10 @@ __device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, d
   }
   PhotAcc A = {0, 0, 0, 0, 0, 0, 0, 0};
   if (blo <= NumBndin1 && bhi >= 1) band_step<ISO, 1, MULTI>(1, c, nflux, act, y, A);
-  for (int b = max(blo, NumBndin1 + 1); b <= min(bhi, NumBndin1 + NumBndin2); b++) band_step<ISO, 2, MULTI>(b, c, nflux, act, y, A);
-  for (int b = max(blo, NumBndin1 + NumBndin2 + 1); b <= bhi; b++) band_step<ISO, 3, MULTI>(b, c, nflux, act, y, A);
+  for (int b = max(blo, NumBndin1 + 1); b <= min(bhi, NumBndin1 + NumBndin2); b++)
+    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 2, MULTI>(b, c, nflux, act, y, A);
+  for (int b = max(blo, NumBndin1 + NumBndin2 + 1); b <= bhi; b++)
+    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 3, MULTI>(b, c, nflux, act, y, A);
   const double rvol = fast_rcp(vol) * scale;
   PhotOut r;
   r.photo_in = A.a_in * scale;

@@ -111,3 +111,32 @@ def test_error_paths_on_a_live_context():
     st = c.evolve3D(0.0, p["dt"], 0)
     assert st["niter"] >= 2
     c.close()
+
+
+def test_three_consecutive_time_steps_stay_in_parity():
+    """The program calls evolve3D once per time step with dr, vol, ndens rescaled by the cosmological expansion in
+    between (C2Ray.F90:322-335, cosmology.f90:159).  Differences must not grow from step to step."""
+    p = synth.make_problem(1, n=16)
+    tables = oracle_setup(p)
+    g = oracle_grid(p)
+    c = c2ray_b200.from_problem(p, tables=tables)
+    ndens, dr, vol, z = p["ndens"].copy(), p["dr"].copy(), p["vol"], p["zred"]
+    for step in range(3):
+        so = g.evolve3d(p["dt"])
+        sg = c.evolve3D(step * p["dt"], p["dt"], 0)
+        xh_o, xhe_o, T_o = g.get_state()
+        xh, xhe, T = c.get_state()
+        assert sg["niter"] == so["niter"] and list(sg["conv_hist"]) == list(so["conv_hist"]), step
+        assert frac_err(xh, xh_o) < 1 and frac_err(xhe, xhe_o) < 1, step
+        assert relerr(T, T_o) < 1.3e-7, step
+        # cosmo_evol: zfactor = (1+z_prev)/(1+z_new); dr*=zfactor, vol*=zfactor^3, ndens/=zfactor^3
+        z_new = z - 0.05
+        zf = (1.0 + z) / (1.0 + z_new)
+        dr = dr * zf; vol = vol * zf ** 3; ndens = ndens / zf ** 3; z = z_new
+        import ctypes
+        O.lib().orc_set_geometry(np.ascontiguousarray(dr).ctypes.data_as(ctypes.c_void_p), ctypes.c_double(vol))
+        O.set_params(False, p["temper_val"], p["clumping"], z, p["H0"], p["Omega0"], True, p["subboxsize"], p["max_subbox"])
+        g.set_state(ndens, xh_o, xhe_o, T_o)
+        c.set_geometry(dr, vol, z)
+        c.set_state(ndens, xh, xhe, T)   # each side continues from its own state
+    c.close()
