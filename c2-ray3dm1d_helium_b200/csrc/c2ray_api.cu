@@ -66,6 +66,8 @@ constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
 
 }  // namespace
 
+constexpr int MAX_SWEEP_GROUPS = 8;
+
 struct c2ray_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -102,6 +104,10 @@ struct c2ray_ctx {
   Slot* d_slots = nullptr;
   int* d_active = nullptr;
   SweepTotals* d_tot = nullptr;
+  SweepTotals* d_gtot = nullptr;            // per stream group
+  cudaStream_t gstream[MAX_SWEEP_GROUPS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_SWEEP_GROUPS] = {};
+  int sweep_groups = 2;                     // env C2RAY_SWEEP_GROUPS
   double* d_scratch = nullptr;
   int slots_cap = 0;
   SweepGeom geom{};
@@ -260,19 +266,34 @@ int rebuild_my_sources(c2ray_ctx* c) {
   return 0;
 }
 
-__global__ void k_pack_tail(const SweepTotals* tot, double* tail) {
-  // [photon_loss(1:47) | sum_nbox] ; only photon_loss(1) is ever filled (evolve_source.F90:233)
+// Sums the per-group totals into the context's aggregate and packs [photon_loss(1:47) | sum_nbox] behind the rate
+// grids; only photon_loss(1) is ever filled (evolve_source.F90:233).
+__global__ void k_pack_tail(const SweepTotals* gtot, int ngroups, SweepTotals* tot, double* tail) {
   const int t = threadIdx.x;
-  if (t == 0) tail[0] = tot->photon_loss;
-  else if (t < NumFreqBnd) tail[t] = 0.0;
-  else if (t == NumFreqBnd) tail[t] = (double)tot->sum_nbox;
+  if (t == 0) {
+    SweepTotals a;
+    a.photon_loss = 0.0; a.sum_nbox = 0; a.updates = 0; a.nactive = 0; a.pad = 0;
+    for (int g = 0; g < ngroups; g++) { a.photon_loss += gtot[g].photon_loss; a.sum_nbox += gtot[g].sum_nbox; a.updates += gtot[g].updates; }
+    *tot = a;
+    tail[0] = a.photon_loss;
+    tail[NumFreqBnd] = (double)a.sum_nbox;
+  } else if (t < NumFreqBnd) tail[t] = 0.0;
 }
 
-// evolve.F90:385 pass_all_sources for this rank's sources (device work only, no host sync)
+#define LAUNCH_S(ctx, strm, kernel, grid, block, ...)     \
+  do {                                                    \
+    kernel<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__);  \
+    (ctx)->launches++;                                    \
+  } while (0)
+
+// evolve.F90:385 pass_all_sources for this rank's sources (device work only, no host sync).
+// The sources of a batch are split into groups that run on separate streams: a shell launch ends with a partially
+// filled last wave (and the innermost shells are a single short wave), so the next group's launch fills the SMs the
+// previous one is draining.  Groups share nothing but the atomically accumulated rate grids.
 int sweep_all(c2ray_ctx* c) {
   int rc = bind(c);
   if (rc) return rc;
-  CK(cudaMemsetAsync(c->d_tot, 0, sizeof(SweepTotals), c->stream));
+  int ngroups = 1;
   if (c->n_mine > 0) {
     const int want = c->par.deterministic ? 1 : std::min(c->n_mine, c->par.max_slots > 0 ? c->par.max_slots : 1024);
     rc = alloc_sweep(c, want);
@@ -286,31 +307,55 @@ int sweep_all(c2ray_ctx* c) {
     }
     GridPtrs G{c->ndens, c->xh_av, c->xhe_av, c->rates, c->d_secion, c->N3};
     const int batch = c->par.deterministic ? 1 : c->slots_cap;
+    ngroups = c->par.deterministic ? 1 : std::max(1, std::min(c->sweep_groups, std::min(batch, c->n_mine)));
     const int max_blocks = 148 * 16;
     const bool multi_sed = c->tab[1][0] != nullptr || c->tab[2][0] != nullptr;  // PL / QPL tables present
+    const size_t slot_stride = (size_t)6 * g.cap;
+    CK(cudaMemsetAsync(c->d_gtot, 0, sizeof(SweepTotals) * MAX_SWEEP_GROUPS, c->stream));
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    for (int q = 0; q < ngroups; q++) CK(cudaStreamWaitEvent(c->gstream[q], c->ev_fork, 0));
     for (int first = 0; first < c->n_mine; first += batch) {
       const int ns = std::min(batch, c->n_mine - first);
-      LAUNCH(c, k_slots_init, (ns + 127) / 128, 128, c->d_slots, ns, c->d_srcids + first, c->d_srcpos, c->d_nf,
-             c->have_pl_flux ? c->d_nfpl : nullptr, c->have_qpl_flux ? c->d_nfqpl : nullptr, c->d_tot, c->d_active);
+      const int per = (ns + ngroups - 1) / ngroups;
+      int goff[MAX_SWEEP_GROUPS], gns[MAX_SWEEP_GROUPS];
+      for (int q = 0; q < ngroups; q++) { goff[q] = std::min(q * per, ns); gns[q] = std::min(per, ns - goff[q]); }
+      for (int q = 0; q < ngroups; q++)
+        if (gns[q] > 0)
+          LAUNCH_S(c, c->gstream[q], k_slots_init, (gns[q] + 127) / 128, 128, c->d_slots + goff[q], gns[q],
+                   c->d_srcids + first + goff[q], c->d_srcpos, c->d_nf, c->have_pl_flux ? c->d_nfpl : nullptr,
+                   c->have_qpl_flux ? c->d_nfqpl : nullptr, c->d_gtot + q, c->d_active + goff[q]);
       const int reach3 = std::min(g.R[2], g.L[2]);
       for (int b = 1;; b++) {
-        LAUNCH(c, k_decide, 1, 256, c->d_slots, ns, g, c->d_tot, c->d_active);
+        for (int q = 0; q < ngroups; q++)
+          if (gns[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q]);
         const int r_lo = b == 1 ? 0 : g.subboxsize * (b - 1) + 1;
         const int r_hi = (int)std::min<long long>((long long)g.subboxsize * b, rmax);
         for (int r = r_lo; r <= r_hi; r++) {
-          const long long items = (long long)ns * (r == 0 ? 1 : 24LL * r * r + 2);
-          const int blocks = (int)std::min<long long>((items + 127) / 128, max_blocks);
-#define SWEEP(ISO, MULTI) LAUNCH(c, (k_sweep_shell<ISO, MULTI>), blocks, 128, c->d_slots, c->d_active, c->d_tot, g, G, c->d_scratch, r)
-          if (multi_sed) { if (c->par.isothermal) SWEEP(true, true); else SWEEP(false, true); }
-          else { if (c->par.isothermal) SWEEP(true, false); else SWEEP(false, false); }
+          for (int q = 0; q < ngroups; q++) {
+            if (gns[q] <= 0) continue;
+            const long long items = (long long)gns[q] * (r == 0 ? 1 : 24LL * r * r + 2);
+            const int blocks = (int)std::min<long long>((items + 127) / 128, max_blocks);
+#define SWEEP(ISO, MULTI)                                                                                              \
+  LAUNCH_S(c, c->gstream[q], (k_sweep_shell<ISO, MULTI>), blocks, 128, c->d_slots + goff[q], c->d_active + goff[q], \
+           c->d_gtot + q, g, G, c->d_scratch + (size_t)goff[q] * slot_stride, r)
+            if (multi_sed) { if (c->par.isothermal) SWEEP(true, true); else SWEEP(false, true); }
+            else { if (c->par.isothermal) SWEEP(true, false); else SWEEP(false, false); }
 #undef SWEEP
+          }
         }
         if ((long long)g.subboxsize * b >= reach3) break;  // the do-while's extent test fails for every source
       }
-      LAUNCH(c, k_decide, 1, 256, c->d_slots, ns, g, c->d_tot, c->d_active);  // close the sources still active
+      for (int q = 0; q < ngroups; q++)  // close the sources still active
+        if (gns[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q]);
     }
+    for (int q = 0; q < ngroups; q++) {
+      CK(cudaEventRecord(c->ev_join[q], c->gstream[q]));
+      CK(cudaStreamWaitEvent(c->stream, c->ev_join[q], 0));
+    }
+  } else {
+    CK(cudaMemsetAsync(c->d_gtot, 0, sizeof(SweepTotals) * MAX_SWEEP_GROUPS, c->stream));
   }
-  LAUNCH(c, k_pack_tail, 1, 64, c->d_tot, c->rates + 4 * c->N3);
+  LAUNCH(c, k_pack_tail, 1, 64, c->d_gtot, ngroups, c->d_tot, c->rates + 4 * c->N3);
   CK(cudaGetLastError());
   return 0;
 }
@@ -419,6 +464,11 @@ int c2ray_b200_init(const c2ray_params* params, const int32_t mesh[3], int32_t d
   CK(cudaMemset(c->rates, 0, c->rates_count * 8));
   CK(cudaMemset(c->temp, 0, 3 * N3 * 4));
   CK(cudaMalloc(&c->d_tot, sizeof(SweepTotals)));
+  CK(cudaMalloc(&c->d_gtot, sizeof(SweepTotals) * MAX_SWEEP_GROUPS));
+  for (auto& st : c->gstream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  for (auto& ev : c->ev_join) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  if (const char* e = getenv("C2RAY_SWEEP_GROUPS")) c->sweep_groups = std::max(1, std::min(MAX_SWEEP_GROUPS, atoi(e)));
   CK(cudaMalloc(&c->d_chem, sizeof(ChemTotals)));
   CK(cudaMalloc(&c->d_sums, 5 * sizeof(double)));
   CK(cudaMalloc(&c->d_next_cell, sizeof(unsigned long long)));
@@ -439,12 +489,15 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   void* ptrs[] = {c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->rates, c->temp, c->snap_xh,
                   c->snap_xhe, c->snap_temp, c->d_srcpos, c->d_nf, c->d_nfpl, c->d_nfqpl, c->d_srcids, c->d_tb, c->d_cool,
-                  c->d_slots, c->d_active, c->d_tot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell};
+                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
   for (int s = 0; s < 3; s++) if (c->packed[s]) cudaFree(c->packed[s]);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_timer) if (ev) cudaEventDestroy(ev);
+  for (auto& st : c->gstream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (auto& ev : c->ev_join) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->stream);
   if (g_bound == c) g_bound = nullptr;
   delete c;
