@@ -47,7 +47,9 @@ class Stats(C.Structure):
                 ("sum_nbox_all", C.c_int64), ("rt_updates", C.c_int64), ("chem_cells", C.c_int64),
                 ("nit_total", C.c_int64), ("photon_loss_all", C.c_double), ("ms_sweep", C.c_double),
                 ("ms_chem", C.c_double), ("ms_allreduce", C.c_double), ("ms_total", C.c_double),
-                ("sums_before", C.c_double * 5), ("sums_after", C.c_double * 5), ("conv_hist", C.c_int32 * MAX_ITER_HIST)]
+                ("sums_before", C.c_double * 5), ("sums_after", C.c_double * 5), ("totrec", C.c_double),
+                ("totcollisions", C.c_double), ("recomions", C.c_double), ("total_ion", C.c_double), ("totalsrc", C.c_double),
+                ("photcons", C.c_double), ("conv_hist", C.c_int32 * MAX_ITER_HIST)]
 
 
 def build(verbose=False):

@@ -88,6 +88,7 @@ struct c2ray_ctx {
   int* d_srcids = nullptr;  // 0-based ids of this rank's sources, in source order
   int n_mine = 0;
   bool have_pl_flux = false, have_qpl_flux = false;
+  double sum_nf[3] = {0, 0, 0};  // sum(NormFlux), sum(NormFluxPL), sum(NormFluxQPL) in source order
   // radiation tables
   double* tab[3][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
   int lo[3] = {1, 1, 1}, hi[3] = {0, 0, 0};
@@ -674,6 +675,12 @@ int c2ray_b200_set_sources(c2ray_ctx* c, int32_t NumSrc, const int32_t* srcpos, 
   if (c->d_srcpos) { cudaFree(c->d_srcpos); c->d_srcpos = nullptr; }
   c->NumSrc = NumSrc;
   c->have_pl_flux = nfpl != nullptr; c->have_qpl_flux = nfqpl != nullptr;
+  c->sum_nf[0] = c->sum_nf[1] = c->sum_nf[2] = 0.0;
+  for (int i = 0; i < NumSrc; i++) {
+    c->sum_nf[0] += nf[i];
+    if (nfpl) c->sum_nf[1] += nfpl[i];
+    if (nfqpl) c->sum_nf[2] += nfqpl[i];
+  }
   if (NumSrc > 0) {
     CK(cudaMalloc(&c->d_srcpos, sizeof(int) * 3 * NumSrc));
     CK(cudaMemcpy(c->d_srcpos, srcpos, sizeof(int) * 3 * NumSrc, cudaMemcpyHostToDevice));
@@ -907,6 +914,23 @@ int c2ray_b200_evolve3d(c2ray_ctx* c, double /*time*/, double dt, int32_t restar
     CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[0])); S.ms_chem += ms;
   }
   if ((rc = state_sums(c, c->xh, c->xhe, S.sums_after))) return rc;  // :225 (state_after on the final xh)
+  {
+    // total_rates(dt, xh_av, xhe_av) with the coefficients the reference's module globals hold at this point
+    const double coef_T = c->par.isothermal ? c->par.temper_val : cht.last_coef_T;
+    CK(cudaMemsetAsync(c->d_sums, 0, 3 * sizeof(double), c->stream));
+    if (coef_T > 0.0) LAUNCH(c, k_total_rates, 148 * 4, 256, c->ndens, c->xh_av, c->xhe_av, c->N3, coef_T, c->d_sums);
+    double t3[3];
+    CK(cudaMemcpyAsync(t3, c->d_sums, sizeof(t3), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    S.totrec = t3[0] * c->vol * dt; S.totcollisions = t3[1] * c->vol * dt; S.recomions = t3[2] * c->vol * dt;   // :201-203
+    // total_ionizations :251-260
+    S.total_ion = (S.sums_before[0] - S.sums_after[0]) + (S.sums_before[2] - S.sums_after[2]) + (S.sums_after[4] - S.sums_before[4]);
+    // report_photonstatistics :280-291
+    S.totalsrc = c->sum_nf[0] * c->S_star[0] * dt;
+    if (c->tab[1][0]) S.totalsrc = S.totalsrc + c->sum_nf[1] * c->S_star[1] * dt;
+    if (c->tab[2][0]) S.totalsrc = S.totalsrc + c->sum_nf[2] * c->S_star[2] * dt;
+    S.photcons = S.totalsrc > 0.0 ? (S.total_ion - S.totcollisions - S.recomions) / S.totalsrc : 0.0;
+  }
   CK(cudaStreamSynchronize(c->stream));
   S.ms_total = S.ms_sweep + S.ms_allreduce + S.ms_chem;
   S.niter = niter; S.conv_flag = conv_flag; S.conv_criterion = conv_criterion;

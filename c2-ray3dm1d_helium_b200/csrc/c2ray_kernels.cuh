@@ -339,6 +339,8 @@ struct ChemTotals {
   int nit_max;
   unsigned long long nit_total;
   unsigned long long nsub_total;  // explicit thermal sub-steps taken (drives the choice of global-pass kernel)
+  double last_coef_T;             // avg_temper of the last ini_rec_colion_factors call of the last mesh cell: the state
+                                  // the reference's module globals are left in (photonstatistics.f90:180-194 reads them)
 };
 
 __global__ void __launch_bounds__(128)
@@ -372,7 +374,8 @@ k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out)
     RecCol rc;
     if (iso) ini_rec_colion_factors(d_run.temper_val, rc);  // mat_ini_test.F90:168
     double avg_temper = temp_av_old, temper1;
-    nit = do_chemistry(dt, n, ion, phiHI, phiHeI, phiHeII, heat, temper_old, avg_temper, temper1, rc, &nsub);
+    nit = do_chemistry(dt, n, ion, phiHI, phiHeI, phiHeII, heat, temper_old, avg_temper, temper1, rc, &nsub,
+                       p == N3 - 1 ? &tot->last_coef_T : nullptr);
     double temp_av_new = temp_av_old;
     if (!iso) {  // set_temperature_point: stored as real(si), read back as such (:404)
       const float t0 = (float)temper1, t1 = (float)avg_temper;
@@ -472,6 +475,7 @@ k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_ou
     // ---- IONIZE: one do_chemistry iteration up to the thermal call (evolve_point.F90:488-600) ---------------------
     if (phase == IONIZE) {
       nit++;
+      if (!iso && (size_t)p == N3 - 1) tot->last_coef_T = avg_temper;
       de = chem_ionization(dt, n, ion, phiHI, phiHeI, phiHeII, avg_temper, temper1, rc, it);
       temper1 = temper0;
       if (iso) {
@@ -551,6 +555,43 @@ __global__ void k_state_sums(const double* __restrict__ ndens, const double* __r
       double v = lane < nw ? sh[q][lane] : 0.0;
       for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
       if (lane == 0) atomicAdd(out5 + q, v);
+    }
+  }
+}
+
+// photonstatistics.f90:150-204 total_rates: recombinations that do not ionize, collisional ionizations and ionizing
+// He recombinations, summed over the mesh with the coefficients the module globals hold (coef_T, see ChemTotals).
+// out3 += (totrec, totcollisions, recomions) before the *vol*dt factor.
+__global__ void k_total_rates(const double* __restrict__ ndens, const double* __restrict__ xh_av,
+                              const double* __restrict__ xhe_av, size_t N3, double coef_T, double* out3) {
+  __shared__ RecCol rcs;
+  __shared__ double sh[3][32];
+  if (threadIdx.x == 0) ini_rec_colion_factors(coef_T, rcs);
+  __syncthreads();
+  const RecCol rc = rcs;
+  const double clumping = d_run.clumping;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N3; p += (size_t)gridDim.x * blockDim.x) {
+    const double n = ndens[p];
+    const double h0 = xh_av[p], h1 = xh_av[p + N3], he0 = xhe_av[p], he1 = xhe_av[p + N3], he2 = xhe_av[p + 2 * N3];
+    const double ne = electrondens(n, h1, he1, he2);
+    s0 += n * (h1 * rc.brech0 * (1.0 - abu_he) + he1 * rc.breche0 * abu_he * 0.04) * ne * clumping;
+    s1 += n * ne * (h0 * rc.colli_HI + he0 * rc.colli_HeI + he1 * rc.colli_HeII);
+    s2 += n * abu_he * clumping * (he2 * 1.121 * rc.breche1 + he1 * rc.breche0 * 0.96) * abu_he * ne;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double v[3] = {s0, s1, s2};
+  for (int q = 0; q < 3; q++) {
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+    if (lane == 0) sh[q][w] = v[q];
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int q = 0; q < 3; q++) {
+      double x = lane < nw ? sh[q][lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) atomicAdd(out3 + q, x);
     }
   }
 }

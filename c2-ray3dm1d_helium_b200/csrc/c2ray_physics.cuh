@@ -397,7 +397,7 @@ __device__ __forceinline__ bool chem_converged(const Ion& ion, const ChemIter& i
 // temper_old: T at the start of the step (grid(..,2)); avg_temper in: grid(..,1)
 __device__ __forceinline__ int do_chemistry(double dt, double n, Ion& ion, double phiHI, double phiHeI, double phiHeII,
                                             double heat, double temper_old, double& avg_temper, double& temper1_out,
-                                            RecCol& rc, int* nsub_total = nullptr) {
+                                            RecCol& rc, int* nsub_total = nullptr, double* last_coef_T = nullptr) {
   const bool iso = d_run.isothermal != 0;
   double temper1 = temper_old;
   const double temper0 = temper1;
@@ -405,6 +405,7 @@ __device__ __forceinline__ int do_chemistry(double dt, double n, Ion& ion, doubl
   for (;;) {
     nit++;
     ChemIter it;
+    if (last_coef_T && !iso) *last_coef_T = avg_temper;  // what the reference's module globals hold afterwards
     const double de = chem_ionization(dt, n, ion, phiHI, phiHeI, phiHeII, avg_temper, temper1, rc, it);
     temper1 = temper0;
     if (!iso) {

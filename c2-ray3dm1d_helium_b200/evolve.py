@@ -204,7 +204,7 @@ class C2Ray:
     def _stats(st):
         d = {k: getattr(st, k) for k in ("niter", "conv_flag", "conv_criterion", "nit_max", "sum_nbox_all", "rt_updates",
                                          "chem_cells", "nit_total", "photon_loss_all", "ms_sweep", "ms_chem", "ms_allreduce",
-                                         "ms_total")}
+                                         "ms_total", "totrec", "totcollisions", "recomions", "total_ion", "totalsrc", "photcons")}
         d["sums_before"] = np.array(st.sums_before[:])
         d["sums_after"] = np.array(st.sums_after[:])
         d["conv_hist"] = np.array(st.conv_hist[:min(st.niter, capi.MAX_ITER_HIST)])

@@ -38,6 +38,7 @@ module c2ray_b200
      integer(c_int64_t) :: sum_nbox_all, rt_updates, chem_cells, nit_total
      real(c_double) :: photon_loss_all, ms_sweep, ms_chem, ms_allreduce, ms_total
      real(c_double) :: sums_before(5), sums_after(5)
+     real(c_double) :: totrec, totcollisions, recomions, total_ion, totalsrc, photcons
      integer(c_int32_t) :: conv_hist(C2RAY_MAX_ITER_HIST)
   end type c2ray_stats
 

@@ -82,6 +82,9 @@ typedef struct c2ray_stats {
   double ms_sweep, ms_chem, ms_allreduce, ms_total; /* CUDA-event device times of this call */
   double sums_before[5];   /* photonstatistics.f90:117 state_before: H0,H+,He0,He+,He++ */
   double sums_after[5];    /* photonstatistics.f90:208 state_after */
+  /* photonstatistics.f90:150-270 for the finished step: total_rates with (xh_av, xhe_av), total_ionizations,
+   * the source photon budget and the photon-conservation ratio written to PhotonCounts.out (:286-298) */
+  double totrec, totcollisions, recomions, total_ion, totalsrc, photcons;
   int32_t conv_hist[C2RAY_MAX_ITER_HIST]; /* conv_flag after iteration i+1 */
 } c2ray_stats;
 

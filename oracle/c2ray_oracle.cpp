@@ -1497,6 +1497,26 @@ void orc_state_sums(const double* xh, const double* xhe, double* out5) {
   out5[2] = s[2] * G.vol * abu_he; out5[3] = s[3] * G.vol * abu_he; out5[4] = s[4] * G.vol * abu_he;
 }
 
+// photonstatistics.f90:150-204 total_rates with the module-global coefficients as the last do_chemistry left them
+// (serial global pass only), then *vol*dt (:201-203).  out3 = totrec, totcollisions, recomions
+void orc_total_rates(double dt, const double* xh_l, const double* xhe_l, double* out3) {
+  const size_t N3 = ncell();
+  double totrec = 0.0, totcollisions = 0.0, recomions = 0.0;
+  const double clumping = (double)G.clumping;
+  for (size_t p = 0; p < N3; p++) {
+    const double yh[2] = {xh_l[p], xh_l[p + N3]};
+    const double yhe[3] = {xhe_l[p], xhe_l[p + N3], xhe_l[p + 2 * N3]};
+    const double ndens_p = G.ndens[p];
+    totrec = totrec + ndens_p * (yh[1] * G.rc.brech0 * (1.0 - abu_he) + yhe[1] * G.rc.breche0 * abu_he * 0.04) *
+                          electrondens(ndens_p, yh, yhe) * clumping;
+    totcollisions = totcollisions + ndens_p * electrondens(ndens_p, yh, yhe) *
+                                        (yh[0] * G.rc.colli_HI + yhe[0] * G.rc.colli_HeI + yhe[1] * G.rc.colli_HeII);
+    recomions = recomions + ndens_p * abu_he * clumping * (yhe[2] * 1.121 * G.rc.breche1 + yhe[1] * G.rc.breche0 * 0.96) *
+                                abu_he * electrondens(ndens_p, yh, yhe);
+  }
+  out3[0] = totrec * G.vol * dt; out3[1] = totcollisions * G.vol * dt; out3[2] = recomions * G.vol * dt;
+}
+
 // mrgrnk.f90:21-215 R_mrgrnk: rank of a real array, stable under ties (merge sort); ranks are 1-based.
 void orc_mrgrnk(int n, const float* x, int* irngt) {
   std::vector<int> idx(n);

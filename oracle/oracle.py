@@ -220,6 +220,12 @@ class Grid:
         return dict(niter=int(stats[0]), conv_flag=int(stats[1]), conv_criterion=int(stats[2]), sum_nbox=int(stats[3]),
                     rt_updates=int(stats[4]), conv_hist=hist[1:int(stats[0]) + 1].copy())
 
+    def total_rates(self, dt, xh_av, xhe_av):
+        out = np.zeros(3)
+        lib().orc_total_rates(C.c_double(dt), np.ascontiguousarray(xh_av).ctypes.data_as(C.c_void_p),
+                              np.ascontiguousarray(xhe_av).ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out
+
     def state_sums(self, xh, xhe):
         out = np.zeros(5)
         lib().orc_state_sums(np.ascontiguousarray(xh).ctypes.data_as(C.c_void_p), np.ascontiguousarray(xhe).ctypes.data_as(C.c_void_p),

@@ -193,6 +193,13 @@ def test_evolve3d(cfg, n, nsrc, iso):
         assert relerr(T, T_o) < 1.3e-7
     # photon statistics sums (photonstatistics.f90:117): summation-order sensitive
     assert relerr(sg["sums_after"], g.state_sums(xh_o, xhe_o), 1e-300) < 1e-9
+    # photon statistics of the finished step (photonstatistics.f90:150-298): recombinations, collisions, conservation
+    tr = g.total_rates(p["dt"], *g.get_work_state()[:2])
+    assert relerr([sg["totrec"], sg["totcollisions"], sg["recomions"]], tr, 1e-300) < 1e-8
+    before = g.state_sums(p["xh"], p["xhe"]); after = g.state_sums(xh_o, xhe_o)
+    total_ion = (before[0] - after[0]) + (before[2] - after[2]) + (after[4] - before[4])
+    assert abs(sg["total_ion"] / total_ion - 1) < 1e-8
+    assert 0.0 < sg["photcons"] < 1.2 and sg["totalsrc"] > 0
     # host-buffer entry point gives the same answer
     xh2, xhe2, T2 = p["xh"].copy(), p["xhe"].copy(), p["temperature_grid"].copy()
     c.evolve3D_host(0.0, p["dt"], 0, p["ndens"], xh2, xhe2, T2)
