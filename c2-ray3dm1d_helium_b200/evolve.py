@@ -325,7 +325,7 @@ def from_problem(p, device=-1, deterministic=False, max_slots=0, tables=None):
     c.setup_cool()
     c.set_geometry(p["dr"], p["vol"], p["zred"])
     if tables is None:
-        c.rad_ini(p["T_eff"], p["S_star"], qpl=p.get("qpl"))
+        c.rad_ini(p["T_eff"], p["S_star"], pl=p.get("pl"), qpl=p.get("qpl"))
     else:
         for sed in range(3):
             t = tables.get(sed)
@@ -333,6 +333,6 @@ def from_problem(p, device=-1, deterministic=False, max_slots=0, tables=None):
                 c.upload_tables(sed, None, None, None, None, 1, 0, 0.0)
             else:
                 c.upload_tables(sed, *t)
-    c.set_sources(p["srcpos"], p["NormFlux"], None, p.get("NormFluxQPL"))
+    c.set_sources(p["srcpos"], p["NormFlux"], p.get("NormFluxPL"), p.get("NormFluxQPL"))
     c.set_state(p["ndens"], p["xh"], p["xhe"], p["temperature_grid"])
     return c

@@ -12,14 +12,18 @@ def oracle_setup(p, isothermal=None):
     global _tables_key
     iso = p["isothermal"] if isothermal is None else isothermal
     qpl = p.get("qpl")
-    key = (p["T_eff"], p["S_star"], None if qpl is None else tuple(sorted(qpl.items())), iso)
+    pl = p.get("pl")
+    key = (p["T_eff"], p["S_star"], None if qpl is None else tuple(sorted(qpl.items())),
+           None if pl is None else tuple(sorted(pl.items())), iso)
     if key != _tables_key:
-        O.rad_ini(p["T_eff"], p["S_star"], qpl=qpl, isothermal=iso)
+        O.rad_ini(p["T_eff"], p["S_star"], pl=pl, qpl=qpl, isothermal=iso)
         _tables_key = key
     O.set_params(iso, p["temper_val"], p["clumping"], p["zred"], p["H0"], p["Omega0"], p["cosmological"],
                  p.get("subboxsize", 10), p.get("max_subbox", 1150))
     info = O.sed_info()
     tables = {0: tuple(O.table(0, k) if (k < 2 or not iso) else None for k in range(4)) + (info["bb"][0], info["bb"][1], p["S_star"])}
+    if pl is not None:
+        tables[1] = tuple(O.table(1, k) if (k < 2 or not iso) else None for k in range(4)) + (info["pl"][0], info["pl"][1], pl["S_star"])
     if qpl is not None:
         tables[2] = tuple(O.table(2, k) if (k < 2 or not iso) else None for k in range(4)) + (info["qpl"][0], info["qpl"][1], qpl["S_star"])
     return tables
@@ -28,7 +32,7 @@ def oracle_setup(p, isothermal=None):
 def oracle_grid(p):
     g = O.Grid(p["mesh"], p["dr"], p["vol"])
     g.set_state(p["ndens"], p["xh"], p["xhe"], p["temperature_grid"])
-    g.set_sources(p["srcpos"], p["NormFlux"], None, p.get("NormFluxQPL"))
+    g.set_sources(p["srcpos"], p["NormFlux"], p.get("NormFluxPL"), p.get("NormFluxQPL"))
     return g
 
 

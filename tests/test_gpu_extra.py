@@ -140,3 +140,53 @@ def test_three_consecutive_time_steps_stay_in_parity():
         c.set_geometry(dr, vol, z)
         c.set_state(ndens, xh, xhe, T)   # each side continues from its own state
     c.close()
+
+
+def test_all_three_seds():
+    """-DPL -DQUASARS build of the reference: black body + power law ("P", index 2.5) + quasar power law ("Q", 1.8)."""
+    p = synth.make_problem(3, n=20, num_src=4)  # 20^3: conv_criterion = min(int(2.5e-4*8000), NumSrc) = 2 > 0
+    p["pl"] = dict(index=2.5, minfreq=p["qpl"]["minfreq"] * 0.2, maxfreq=p["qpl"]["maxfreq"], S_star=1e48)
+    p["NormFluxPL"] = np.array([0.0, 2.0e5, 0.0, 5.0e4])
+    p["NormFluxQPL"] = np.array([1.0e5, 0.0, 0.0, 3.0e4])
+    p["NormFlux"] = np.array([3.0e6, 0.0, 2.0e6, 1.0e6])   # source 2 has no black-body component at all
+    tables = oracle_setup(p)
+    info = O.sed_info()
+    assert info["pl"][0] < info["qpl"][0] and info["pl"][1] == 47
+    # photoion_rates with the three SEDs together
+    rng = np.random.default_rng(5)
+    n = 4000
+    lin = 10.0 ** rng.uniform(10, 23, (n, 3)); d = 10.0 ** rng.uniform(9, 21, (n, 3))
+    col6 = np.empty((n, 6)); col6[:, 0::2] = lin; col6[:, 1::2] = lin + d
+    vol = 10.0 ** rng.uniform(62, 68, n); i_state = 10.0 ** rng.uniform(-10, 0, n) * 0.999
+    c = c2ray_b200.from_problem(p, tables=tables)
+    for nflux in ([2e5, 3e4, 1e4], [0.0, 3e4, 0.0], [0.0, 0.0, 1e4]):
+        got = c.photoion_rates(col6, vol, nflux, i_state)
+        ref = O.photoion_rates_batch(col6, vol, nflux, i_state)
+        scale = np.abs(ref).max(axis=0)
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6 * scale + 1e-300)) < 1e-8, nflux
+    # a full step with gentler hard-spectrum sources (56 global iterations in the oracle)
+    p["NormFluxPL"] = np.array([0.0, 2.0e3, 0.0, 5.0e2])
+    p["NormFluxQPL"] = np.array([1.0e3, 0.0, 0.0, 3.0e2])
+    c.set_sources(p["srcpos"], p["NormFlux"], p["NormFluxPL"], p["NormFluxQPL"])
+    g = oracle_grid(p)
+    so = g.evolve3d(p["dt"])
+    assert so["niter"] < 100
+    sg = c.evolve3D(0.0, p["dt"], 0)
+    xh_o, xhe_o, T_o = g.get_state()
+    xh, xhe, T = c.get_state()
+    assert sg["niter"] == so["niter"] and list(sg["conv_hist"]) == list(so["conv_hist"]) and sg["rt_updates"] == so["rt_updates"]
+    # In this hard-spectrum case a handful of cells run do_chemistry to its 401-iteration limit without converging (in the
+    # oracle too: tools/diag_evolve.py), i.e. they sit on a limit cycle that amplifies last-digit differences during the
+    # intermediate global iterations (up to 1e-4); the converged end state still agrees to a few 1e-10.
+    assert frac_err(xh, xh_o) < 5 and frac_err(xhe, xhe_o) < 5 and relerr(T, T_o) < 1e-6
+    for a, b in zip(c.get_rates(), g.get_rates()):
+        assert relerr(a, b, 1e-6 * np.abs(b).max() + 1e-300) < 1e-5  # rate grids of the last iteration: computed from the second-to-last, not yet settled, state
+    # device rad_ini with all three SEDs against the oracle's tables
+    c2 = c2ray_b200.from_problem(p)
+    for sed in range(3):
+        for kind in range(4):
+            got, lo, hi, S = c2.download_table(sed, kind)
+            ref = O.table(sed, kind)
+            scale = np.abs(ref).max(axis=1, keepdims=True)
+            assert np.max(np.abs(got - ref) / (np.abs(ref) + 1e-250 + 1e-14 * scale)) < 1e-9, (sed, kind)
+    c.close(); c2.close()
