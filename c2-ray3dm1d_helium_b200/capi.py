@@ -22,6 +22,9 @@ EXPORTS = [
     "c2ray_b200_comm_unique_id", "c2ray_b200_comm_init", "c2ray_b200_set_rank", "c2ray_b200_rates_device_buffer",
     "c2ray_b200_bench_global_pass", "c2ray_b200_launch_count", "c2ray_b200_measure_fp64", "c2ray_b200_stream",
     "c2ray_b200_timer_start", "c2ray_b200_timer_stop",
+    "c2ray_b200_set_dump", "c2ray_b200_write_iteration_dump", "c2ray_b200_read_iteration_dump",
+    "c2ray_b200_write_stream2", "c2ray_b200_write_stream3", "c2ray_b200_fortran_records_write",
+    "c2ray_b200_fortran_records_read",
 ]
 
 

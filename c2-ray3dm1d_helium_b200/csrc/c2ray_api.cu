@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +17,7 @@
 
 #include "../../include/c2ray_b200.h"
 #include "band_data.h"
+#include "c2ray_io.h"
 #include "c2ray_kernels.cuh"
 
 using namespace c2;
@@ -41,6 +43,10 @@ struct NcclApi {
   int (*GetUniqueId)(nccl_uid*) = nullptr;
   int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(nccl_comm) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 } g_nccl;
@@ -56,13 +62,18 @@ int nccl_load() {
   g_nccl.GetUniqueId = (int (*)(nccl_uid*))dlsym(g_nccl.h, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))dlsym(g_nccl.h, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.ReduceScatter = (int (*)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(g_nccl.h, "ncclReduceScatter");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm, cudaStream_t))dlsym(g_nccl.h, "ncclAllGather");
+  g_nccl.GroupStart = (int (*)())dlsym(g_nccl.h, "ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.h, "ncclGroupEnd");
   g_nccl.CommDestroy = (int (*)(nccl_comm))dlsym(g_nccl.h, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.ReduceScatter ||
+      !g_nccl.AllGather || !g_nccl.GroupStart || !g_nccl.GroupEnd)
     return fail(C2RAY_ERR_NCCL, "libnccl: missing symbols");
   return 0;
 }
-constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+constexpr int NCCL_INT32 = 2, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
 
 }  // namespace
 
@@ -106,11 +117,13 @@ struct c2ray_ctx {
   int* d_active = nullptr;
   SweepTotals* d_tot = nullptr;
   SweepTotals* d_gtot = nullptr;            // per stream group
+  int* h_nact = nullptr;                    // pinned: active sources per group after a sub-box decision
   cudaStream_t gstream[MAX_SWEEP_GROUPS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_SWEEP_GROUPS] = {};
   int sweep_groups = 2;                     // env C2RAY_SWEEP_GROUPS
   double* d_scratch = nullptr;
   int slots_cap = 0;
+  bool slots_budget_limited = false;
   SweepGeom geom{};
   ChemTotals* d_chem = nullptr;
   double* d_sums = nullptr;
@@ -122,10 +135,17 @@ struct c2ray_ctx {
   // multi-GPU
   int rank = 0, npr = 1;
   nccl_comm comm = nullptr;
+  int split_chem = 1;          // env C2RAY_SPLIT_CHEM: evolve3d splits the global pass over the ranks (see split_active)
+  double* d_chemred = nullptr; // 4 sums (FP64) + 1 maximum (int32) of the global-pass counters, for the cross-rank combination
+  // iteration dumps (evolve.F90:233-367) and output streams (output.F90:249-379)
+  std::string dump_dir;
+  double dump_interval_s = -1.0;  // < 0: no dumps; the reference writes one when 15 minutes have passed (:207)
+  int ndump = 0;                  // evolve.F90:239, saved between calls
+  void* h_stage = nullptr;        // pinned staging buffer for device <-> file traffic
   // bookkeeping
   int64_t launches = 0;
   bool run_dirty = true;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_timer[2] = {nullptr, nullptr};
 };
 
@@ -240,7 +260,8 @@ int alloc_sweep(c2ray_ctx* c, int want_slots) {
   }
   c->geom.subboxsize = c->par.subboxsize;
   const int cap = rmax == 0 ? 1 : 24 * rmax * rmax + 2;
-  if (c->d_scratch && cap == c->geom.cap && want_slots <= c->slots_cap) return 0;
+  // slots_cap below the request means the scratch budget, not the request, set it: asking again changes nothing
+  if (c->d_scratch && cap == c->geom.cap && (want_slots <= c->slots_cap || c->slots_budget_limited)) return 0;
   c->geom.cap = cap;
   if (c->d_scratch) { cudaFree(c->d_scratch); cudaFree(c->d_slots); cudaFree(c->d_active); c->d_scratch = nullptr; }
   size_t per_slot = (size_t)6 * cap * sizeof(double);
@@ -252,6 +273,7 @@ int alloc_sweep(c2ray_ctx* c, int want_slots) {
   CK(cudaMalloc(&c->d_slots, sizeof(Slot) * slots));
   CK(cudaMalloc(&c->d_active, sizeof(int) * slots));
   c->slots_cap = slots;
+  c->slots_budget_limited = slots < want_slots;
   return 0;
 }
 
@@ -326,15 +348,28 @@ int sweep_all(c2ray_ctx* c) {
                    c->d_srcids + first + goff[q], c->d_srcpos, c->d_nf, c->have_pl_flux ? c->d_nfpl : nullptr,
                    c->have_qpl_flux ? c->d_nfqpl : nullptr, c->d_gtot + q, c->d_active + goff[q]);
       const int reach3 = std::min(g.R[2], g.L[2]);
+      int nact[MAX_SWEEP_GROUPS];
+      for (int q = 0; q < ngroups; q++) nact[q] = gns[q];
       for (int b = 1;; b++) {
         for (int q = 0; q < ngroups; q++)
-          if (gns[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q]);
+          if (nact[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q]);
+        if (b > 1) {
+          // From the second sub-box on most sources have dropped out (photon loss below 1e-10 of the flux): fetch the
+          // number still active so that the shells of a level nobody traces are not launched at all and the grids
+          // of the others are sized to the work that exists.  One short host wait per sub-box level.
+          for (int q = 0; q < ngroups; q++)
+            if (nact[q] > 0) CK(cudaMemcpyAsync(c->h_nact + q, &c->d_gtot[q].nactive, sizeof(int), cudaMemcpyDeviceToHost, c->gstream[q]));
+          bool any = false;
+          for (int q = 0; q < ngroups; q++)
+            if (nact[q] > 0) { CK(cudaStreamSynchronize(c->gstream[q])); nact[q] = c->h_nact[q]; any = any || nact[q] > 0; }
+          if (!any) break;
+        }
         const int r_lo = b == 1 ? 0 : g.subboxsize * (b - 1) + 1;
         const int r_hi = (int)std::min<long long>((long long)g.subboxsize * b, rmax);
         for (int r = r_lo; r <= r_hi; r++) {
           for (int q = 0; q < ngroups; q++) {
-            if (gns[q] <= 0) continue;
-            const long long items = (long long)gns[q] * (r == 0 ? 1 : 24LL * r * r + 2);
+            if (nact[q] <= 0) continue;
+            const long long items = (long long)nact[q] * (r == 0 ? 1 : 24LL * r * r + 2);
             const int blocks = (int)std::min<long long>((items + 127) / 128, max_blocks);
 #define SWEEP(ISO, MULTI)                                                                                              \
   LAUNCH_S(c, c->gstream[q], (k_sweep_shell<ISO, MULTI>), blocks, 128, c->d_slots + goff[q], c->d_active + goff[q], \
@@ -347,7 +382,7 @@ int sweep_all(c2ray_ctx* c) {
         if ((long long)g.subboxsize * b >= reach3) break;  // the do-while's extent test fails for every source
       }
       for (int q = 0; q < ngroups; q++)  // close the sources still active
-        if (gns[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q]);
+        if (nact[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q]);
     }
     for (int q = 0; q < ngroups; q++) {
       CK(cudaEventRecord(c->ev_join[q], c->gstream[q]));
@@ -368,7 +403,190 @@ int allreduce_rates(c2ray_ctx* c) {  // evolve.F90:505-548
   return 0;
 }
 
-int global_pass_launch(c2ray_ctx* c, double dt, int* d_nit) {
+// ---- files ------------------------------------------------------------------------------------------------------
+constexpr size_t STAGE_BYTES = (size_t)64 << 20;
+
+int ensure_stage(c2ray_ctx* c) {
+  if (!c->h_stage) CK(cudaMallocHost(&c->h_stage, STAGE_BYTES));
+  return 0;
+}
+
+// appends `bytes` of device memory to the record being written; to_f32: the source is FP64 and the file gets real(x)
+int put_device(c2ray_ctx* c, c2io::RecordWriter& w, const void* dptr, size_t bytes, bool to_f32 = false) {
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  const char* d = static_cast<const char*>(dptr);
+  for (size_t off = 0; off < bytes; off += STAGE_BYTES) {
+    const size_t k = std::min(STAGE_BYTES, bytes - off);
+    CK(cudaMemcpyAsync(c->h_stage, d + off, k, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (to_f32) {
+      const double* src = static_cast<const double*>(c->h_stage);
+      float* dst = static_cast<float*>(c->h_stage);  // in place: element i is read before slot i/2 is overwritten
+      const size_t n = k / 8;
+      for (size_t i = 0; i < n; i++) { const double v = src[i]; dst[i] = (float)v; }
+      if (!w.put(dst, n * 4)) return fail(C2RAY_ERR_STATE, "short write");
+    } else if (!w.put(c->h_stage, k)) {
+      return fail(C2RAY_ERR_STATE, "short write");
+    }
+  }
+  return 0;
+}
+
+int get_device(c2ray_ctx* c, c2io::RecordReader& r, void* dptr, size_t bytes) {
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  char* d = static_cast<char*>(dptr);
+  for (size_t off = 0; off < bytes; off += STAGE_BYTES) {
+    const size_t k = std::min(STAGE_BYTES, bytes - off);
+    if (!r.get(c->h_stage, k)) return fail(C2RAY_ERR_STATE, "iteration dump: record does not match this mesh / isothermal setting");
+    CK(cudaMemcpyAsync(d + off, c->h_stage, k, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+std::string join_dir(const std::string& dir, const std::string& name) {
+  // the reference concatenates trim(adjustl(dump_dir))//iterfile, i.e. the directory string carries its own separator
+  if (dir.empty() || dir.back() == '/') return dir + name;
+  return dir + "/" + name;
+}
+
+// evolve.F90:233-275 write_iteration_dump: niter, photon_loss_all, phih_grid, xh_av, xh_intermed, phihe_grid, xhe_av,
+// xhe_intermed [, phiheat, temperature_grid]
+int write_iteration_dump_file(c2ray_ctx* c, const std::string& path, int niter) {
+  const size_t N3 = c->N3;
+  c2io::RecordWriter w;
+  if (!w.open(path)) return fail(C2RAY_ERR_STATE, "cannot open " + path + " for writing");
+  int rc;
+  const int32_t ni = niter;
+  if (!w.record(&ni, 4)) return fail(C2RAY_ERR_STATE, "short write");
+  if (!w.begin(NumFreqBnd * 8) || (rc = put_device(c, w, c->rates + 4 * N3, NumFreqBnd * 8))) return rc ? rc : fail(C2RAY_ERR_STATE, "short write");
+  struct Rec { const void* p; size_t bytes; };
+  const Rec recs[] = {{c->rates, N3 * 8},          {c->xh_av, 2 * N3 * 8},  {c->xh_int, 2 * N3 * 8}, {c->rates + N3, 2 * N3 * 8},
+                      {c->xhe_av, 3 * N3 * 8},     {c->xhe_int, 3 * N3 * 8}, {c->rates + 3 * N3, N3 * 8}, {c->temp, 3 * N3 * 4}};
+  const int nrec = c->par.isothermal ? 6 : 8;
+  for (int i = 0; i < nrec; i++) {
+    if (!w.begin(recs[i].bytes)) return fail(C2RAY_ERR_STATE, "short write");
+    if ((rc = put_device(c, w, recs[i].p, recs[i].bytes))) return rc;
+  }
+  if (!w.close()) return fail(C2RAY_ERR_STATE, "error closing " + path);
+  return 0;
+}
+
+// evolve.F90:279-367 start_from_dump (every rank reads the file itself instead of rank 0 reading and broadcasting)
+int read_iteration_dump_file(c2ray_ctx* c, const std::string& path, int* niter) {
+  const size_t N3 = c->N3;
+  c2io::RecordReader r;
+  if (!r.open(path)) return fail(C2RAY_ERR_STATE, "cannot open iteration dump " + path);
+  int32_t ni = 0;
+  if (!r.record(&ni, 4)) return fail(C2RAY_ERR_STATE, "iteration dump: bad first record in " + path);
+  int rc;
+  if (!r.begin(NumFreqBnd * 8)) return fail(C2RAY_ERR_STATE, "iteration dump: bad photon_loss record");
+  if ((rc = get_device(c, r, c->rates + 4 * N3, NumFreqBnd * 8))) return rc;
+  struct Rec { void* p; size_t bytes; };
+  const Rec recs[] = {{c->rates, N3 * 8},          {c->xh_av, 2 * N3 * 8},  {c->xh_int, 2 * N3 * 8}, {c->rates + N3, 2 * N3 * 8},
+                      {c->xhe_av, 3 * N3 * 8},     {c->xhe_int, 3 * N3 * 8}, {c->rates + 3 * N3, N3 * 8}, {c->temp, 3 * N3 * 4}};
+  const int nrec = c->par.isothermal ? 6 : 8;
+  for (int i = 0; i < nrec; i++) {
+    if (!r.begin(recs[i].bytes)) return fail(C2RAY_ERR_STATE, "iteration dump: record does not match this mesh / isothermal setting");
+    if ((rc = get_device(c, r, recs[i].p, recs[i].bytes))) return rc;
+  }
+  if (niter) *niter = ni;
+  return 0;
+}
+
+// output.F90: write(unit) mesh(1),mesh(2),mesh(3) ; write(unit) (((a(i,j,k),i=..),j=..),k=..)
+int write_plane_file(c2ray_ctx* c, const std::string& path, const void* dplane, size_t elem_bytes, bool to_f32) {
+  c2io::RecordWriter w;
+  if (!w.open(path)) return fail(C2RAY_ERR_STATE, "cannot open " + path + " for writing");
+  const int32_t m[3] = {c->mesh[0], c->mesh[1], c->mesh[2]};
+  if (!w.record(m, 12)) return fail(C2RAY_ERR_STATE, "short write");
+  if (!w.begin(c->N3 * (to_f32 ? 4 : elem_bytes))) return fail(C2RAY_ERR_STATE, "short write");
+  int rc = put_device(c, w, dplane, c->N3 * elem_bytes, to_f32);
+  if (rc) return rc;
+  if (!w.close()) return fail(C2RAY_ERR_STATE, "error closing " + path);
+  return 0;
+}
+
+#define NC(call)                                                                                              \
+  do {                                                                                                        \
+    int r_ = (call);                                                                                          \
+    if (r_ != 0)                                                                                              \
+      return fail(C2RAY_ERR_NCCL, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?")); \
+  } while (0)
+
+// ---- the global pass split over the ranks ------------------------------------------------------
+// The reference runs the global pass replicated on every rank after an allreduce of the four rate grids
+// (evolve.F90:477-548).  Cells are independent there, so with a communicator attached evolve3d gives rank r the cells
+// [r*N3/npr, (r+1)*N3/npr) of every plane: the allreduce becomes its first half (reduce-scatter: a rank only needs the
+// summed rates of its own cells), the pass runs on 1/npr of the mesh, and the second half (all-gather) moves the four
+// planes the next sweep reads -- xh_av(0:1), xhe_av(0:1) -- instead of the rates.  Same bytes on the wire as the
+// allreduce, 1/npr of the chemistry.  The planes the sweep does not read are gathered once, when the iteration ends.
+bool split_active(const c2ray_ctx* c) { return c->comm && c->npr > 1 && c->split_chem && c->N3 % (size_t)c->npr == 0; }
+
+int reduce_scatter_rates(c2ray_ctx* c) {
+  const size_t chunk = c->N3 / c->npr;
+  const int planes = c->par.isothermal ? 3 : 4;
+  NC(g_nccl.GroupStart());
+  for (int q = 0; q < planes; q++) {
+    double* plane = c->rates + (size_t)q * c->N3;
+    NC(g_nccl.ReduceScatter(plane, plane + (size_t)c->rank * chunk, chunk, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+  }
+  double* tail = c->rates + 4 * c->N3;  // photon_loss(1:47), sum_nbox: every rank needs them
+  NC(g_nccl.AllReduce(tail, tail, NumFreqBnd + 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+  NC(g_nccl.GroupEnd());
+  return 0;
+}
+
+int allgather_f64(c2ray_ctx* c, double* const* planes, int n) {
+  const size_t chunk = c->N3 / c->npr;
+  NC(g_nccl.GroupStart());
+  for (int q = 0; q < n; q++)
+    NC(g_nccl.AllGather(planes[q] + (size_t)c->rank * chunk, planes[q], chunk, NCCL_FLOAT64, c->comm, c->stream));
+  NC(g_nccl.GroupEnd());
+  return 0;
+}
+
+// conv_flag, sum(nit), sum(thermal sub-steps), last_coef_T: sums over ranks; nit_max: maximum
+int combine_chem_totals(c2ray_ctx* c) {
+  int* d_max = reinterpret_cast<int*>(c->d_chemred + 4);
+  LAUNCH(c, k_chem_pack, 1, 1, c->d_chem, c->d_chemred, d_max);
+  NC(g_nccl.GroupStart());
+  NC(g_nccl.AllReduce(c->d_chemred, c->d_chemred, 4, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+  NC(g_nccl.AllReduce(d_max, d_max, 1, NCCL_INT32, NCCL_MAX, c->comm, c->stream));
+  NC(g_nccl.GroupEnd());
+  LAUNCH(c, k_chem_unpack, 1, 1, c->d_chem, c->d_chemred, d_max);
+  return 0;
+}
+
+// what the sweep of the next iteration reads
+int allgather_sweep_inputs(c2ray_ctx* c) {
+  double* planes[4] = {c->xh_av, c->xh_av + c->N3, c->xhe_av, c->xhe_av + c->N3};
+  return allgather_f64(c, planes, 4);
+}
+
+// everything else a rank owns only its share of, once the iteration has ended: xh_intermed, xhe_intermed, xhe_av(2),
+// temperature_grid(0:1) and the summed rate grids (output.F90:354,364 writes them)
+int allgather_final(c2ray_ctx* c) {
+  const size_t N3 = c->N3, chunk = N3 / c->npr;
+  double* planes[10] = {c->xh_int, c->xh_int + N3, c->xhe_int, c->xhe_int + N3, c->xhe_int + 2 * N3, c->xhe_av + 2 * N3,
+                        c->rates, c->rates + N3, c->rates + 2 * N3, c->rates + 3 * N3};
+  int rc = allgather_f64(c, planes, c->par.isothermal ? 9 : 10);
+  if (rc) return rc;
+  if (!c->par.isothermal) {
+    NC(g_nccl.GroupStart());
+    for (int q = 0; q < 2; q++)
+      NC(g_nccl.AllGather(c->temp + (size_t)q * N3 + (size_t)c->rank * chunk, c->temp + (size_t)q * N3, chunk, NCCL_FLOAT32,
+                          c->comm, c->stream));
+    NC(g_nccl.GroupEnd());
+  }
+  return 0;
+}
+
+int global_pass_launch(c2ray_ctx* c, double dt, int* d_nit, size_t p_begin = 0, size_t p_end = 0) {
+  if (p_end == 0) p_end = c->N3;
+  const size_t ncell = p_end - p_begin;
   int rc = bind(c);
   if (rc) return rc;
   if (!c->par.isothermal && !c->have_cool) return fail(C2RAY_ERR_STATE, "cooling tables not set (c2ray_b200_set_cooling_tables)");
@@ -386,11 +604,11 @@ int global_pass_launch(c2ray_ctx* c, double dt, int* d_nit) {
       CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
       per_sm = std::max(per_sm, 1);
     }
-    const unsigned blocks = (unsigned)std::min<size_t>((c->N3 + 127) / 128, (size_t)n_sm * per_sm);
-    LAUNCH(c, k_global_pass_q, blocks, 128, P, dt, c->d_chem, d_nit, c->d_next_cell);
+    const unsigned blocks = (unsigned)std::min<size_t>((ncell + 127) / 128, (size_t)n_sm * per_sm);
+    LAUNCH(c, k_global_pass_q, blocks, 128, P, dt, c->d_chem, d_nit, c->d_next_cell, p_begin, p_end);
   } else {
-    const unsigned blocks = (unsigned)((c->N3 + 127) / 128);
-    LAUNCH(c, k_global_pass, blocks, 128, P, dt, c->d_chem, d_nit);
+    const unsigned blocks = (unsigned)((ncell + 127) / 128);
+    LAUNCH(c, k_global_pass, blocks, 128, P, dt, c->d_chem, d_nit, p_begin, p_end);
   }
   CK(cudaGetLastError());
   return 0;
@@ -466,6 +684,7 @@ int c2ray_b200_init(const c2ray_params* params, const int32_t mesh[3], int32_t d
   CK(cudaMemset(c->temp, 0, 3 * N3 * 4));
   CK(cudaMalloc(&c->d_tot, sizeof(SweepTotals)));
   CK(cudaMalloc(&c->d_gtot, sizeof(SweepTotals) * MAX_SWEEP_GROUPS));
+  CK(cudaMallocHost(&c->h_nact, sizeof(int) * MAX_SWEEP_GROUPS));
   for (auto& st : c->gstream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   for (auto& ev : c->ev_join) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -473,6 +692,8 @@ int c2ray_b200_init(const c2ray_params* params, const int32_t mesh[3], int32_t d
   CK(cudaMalloc(&c->d_chem, sizeof(ChemTotals)));
   CK(cudaMalloc(&c->d_sums, 5 * sizeof(double)));
   CK(cudaMalloc(&c->d_next_cell, sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->d_chemred, 6 * sizeof(double)));
+  if (const char* e = getenv("C2RAY_SPLIT_CHEM")) c->split_chem = atoi(e);
   if (const char* e = getenv("C2RAY_CHEM_QUEUE")) c->chem_mode = atoi(e);
   CK(cudaMalloc(&c->d_cool, 5 * TEMPPOINTS * sizeof(double)));
   CK(cudaMalloc(&c->d_tb, sizeof(TableBuild)));
@@ -490,10 +711,12 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   void* ptrs[] = {c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->rates, c->temp, c->snap_xh,
                   c->snap_xhe, c->snap_temp, c->d_srcpos, c->d_nf, c->d_nfpl, c->d_nfqpl, c->d_srcids, c->d_tb, c->d_cool,
-                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell};
+                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell, c->d_chemred};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
   for (int s = 0; s < 3; s++) if (c->packed[s]) cudaFree(c->packed[s]);
+  if (c->h_nact) cudaFreeHost(c->h_nact);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_timer) if (ev) cudaEventDestroy(ev);
   for (auto& st : c->gstream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -868,28 +1091,62 @@ int c2ray_b200_state_sums(c2ray_ctx* c, int32_t which, double out5[5]) {
 
 int c2ray_b200_evolve3d(c2ray_ctx* c, double /*time*/, double dt, int32_t restart, c2ray_stats* st) {
   if (!c) return fail(C2RAY_ERR_ARG, "null argument");
-  if (restart != 0) return fail(C2RAY_ERR_ARG, "restart from iteration dumps is not supported (evolve.F90:279)");
+  if (restart < 0 || restart > 3) return fail(C2RAY_ERR_ARG, "restart must be 0 (fresh step) or 1, 2, 3 (iterdump1.bin, iterdump2.bin, iterdump.bin; evolve.F90:300-307)");
+  if (restart != 0 && c->dump_dir.empty()) return fail(C2RAY_ERR_STATE, "restart requested but no dump directory set (c2ray_b200_set_dump)");
+  auto wallclock1 = std::chrono::steady_clock::now();  // evolve.F90:122
   if (c->NumSrc > 0 && !c->tab[0][0] && !c->tab[1][0] && !c->tab[2][0]) return fail(C2RAY_ERR_STATE, "no radiation tables");
   CK(cudaSetDevice(c->device));
   c2ray_stats S;
   memset(&S, 0, sizeof(S));
   int rc;
   if ((rc = state_sums(c, c->xh, c->xhe, S.sums_before))) return rc;  // evolve.F90:127
-  if ((rc = begin_step(c))) return rc;
   int niter = 0;
   // conv_flag=mesh(1)*mesh(2)*mesh(3) ; conv_criterion=min(int(convergence_fraction*mesh1*mesh2*mesh3),NumSrc)  :136,:147
   int conv_flag = c->mesh[0] * c->mesh[1] * c->mesh[2];
+  if (restart == 0) {
+    if ((rc = begin_step(c))) return rc;
+  }
   const int conv_criterion = std::min((int)(convergence_fraction * c->mesh[0] * c->mesh[1] * c->mesh[2]), c->NumSrc);
   float ms;
   SweepTotals swt;
   memset(&swt, 0, sizeof(swt));
   ChemTotals cht;
   memset(&cht, 0, sizeof(cht));
+  const bool split = split_active(c);
+  const size_t chunk = split ? c->N3 / c->npr : c->N3;
+  // the global pass of one iteration: on this rank's cells + counters + the next sweep's inputs when split over the
+  // ranks, on the whole mesh otherwise.  Records ev[4] after the chemistry kernel.
+  auto chem_phase = [&]() -> int {
+    int r;
+    if (split) {
+      if ((r = global_pass_launch(c, dt, nullptr, (size_t)c->rank * chunk, (size_t)(c->rank + 1) * chunk))) return r;  // :217
+      CK(cudaEventRecord(c->ev[4], c->stream));
+      if ((r = combine_chem_totals(c))) return r;
+      if ((r = allgather_sweep_inputs(c))) return r;
+    } else {
+      if ((r = global_pass_launch(c, dt, nullptr))) return r;  // :217
+      CK(cudaEventRecord(c->ev[4], c->stream));
+    }
+    CK(cudaMemcpyAsync(&cht, c->d_chem, sizeof(cht), cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+  };
+  if (restart != 0) {
+    // evolve.F90:137-141: reload xh_av, xh_intermed, rates, photon_loss, niter ; call global_pass (conv_flag,dt)
+    static const char* names[4] = {"", "iterdump1.bin", "iterdump2.bin", "iterdump.bin"};
+    if ((rc = read_iteration_dump_file(c, join_dir(c->dump_dir, names[restart]), &niter))) return rc;
+    if ((rc = chem_phase())) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    conv_flag = cht.conv_flag;
+    c->last_nsub_per_cell = (double)cht.nsub_total / (double)c->N3;
+    S.chem_cells += (int64_t)chunk;
+  }
   for (;;) {
-    if (conv_flag < conv_criterion && niter > 1) {  // :163
-      if ((rc = end_step(c))) return rc;
+    const bool converged = conv_flag < conv_criterion && niter > 1;  // :163
+    if (converged || niter > 500) {                                  // :177
+      if (split && (rc = allgather_final(c))) return rc;
+      if (converged && (rc = end_step(c))) return rc;
       break;
-    } else if (niter > 500) break;  // :177
+    }
     niter++;
     CK(cudaEventRecord(c->ev[1], c->stream));
     CK(cudaMemsetAsync(c->rates, 0, c->rates_count * 8, c->stream));  // :188
@@ -898,20 +1155,44 @@ int c2ray_b200_evolve3d(c2ray_ctx* c, double /*time*/, double dt, int32_t restar
       CK(cudaMemcpyAsync(&swt, c->d_tot, sizeof(swt), cudaMemcpyDeviceToHost, c->stream));
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
-    if (c->NumSrc > 0 && (rc = allreduce_rates(c))) return rc;
+    if (c->NumSrc > 0) {
+      if (split) rc = reduce_scatter_rates(c); else rc = allreduce_rates(c);
+      if (rc) return rc;
+      // evolve.F90:199-213: rank 0 writes an iteration dump when more than the interval (15 minutes) has passed
+      if (c->dump_interval_s >= 0.0 && !c->dump_dir.empty()) {
+        int due = 0;
+        const auto wallclock2 = std::chrono::steady_clock::now();
+        if (c->rank == 0 && std::chrono::duration<double>(wallclock2 - wallclock1).count() > c->dump_interval_s) due = 1;
+        if (c->comm && c->npr > 1) {  // rank 0's clock decides for everybody
+          int* d_flag = reinterpret_cast<int*>(c->d_chemred + 5);
+          CK(cudaMemcpyAsync(d_flag, &due, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+          NC(g_nccl.AllReduce(d_flag, d_flag, 1, NCCL_INT32, NCCL_SUM, c->comm, c->stream));
+          CK(cudaMemcpyAsync(&due, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+          CK(cudaStreamSynchronize(c->stream));
+        }
+        if (due) {
+          if (split && (rc = allgather_final(c))) return rc;  // rank 0 needs every cell of what it writes
+          if (c->rank == 0) {
+            c->ndump++;  // :243-248
+            if ((rc = write_iteration_dump_file(c, join_dir(c->dump_dir, c->ndump % 2 == 0 ? "iterdump2.bin" : "iterdump1.bin"), niter))) return rc;
+          }
+          wallclock1 = wallclock2;
+        }
+      }
+    }
     CK(cudaEventRecord(c->ev[3], c->stream));
-    if ((rc = global_pass_launch(c, dt, nullptr))) return rc;  // :217
-    CK(cudaMemcpyAsync(&cht, c->d_chem, sizeof(cht), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = chem_phase())) return rc;
     CK(cudaEventRecord(c->ev[0], c->stream));  // iteration end
     CK(cudaStreamSynchronize(c->stream));
     conv_flag = cht.conv_flag;
     c->last_nsub_per_cell = (double)cht.nsub_total / (double)c->N3;
     if (niter <= C2RAY_MAX_ITER_HIST) S.conv_hist[niter - 1] = conv_flag;
     S.rt_updates += (int64_t)swt.updates;
-    S.chem_cells += (int64_t)c->N3;
+    S.chem_cells += (int64_t)chunk;
     CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); S.ms_sweep += ms;
     CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); S.ms_allreduce += ms;
-    CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[0])); S.ms_chem += ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); S.ms_chem += ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[0])); S.ms_allreduce += ms;  // counters + all-gather (split pass only)
   }
   if ((rc = state_sums(c, c->xh, c->xhe, S.sums_after))) return rc;  // :225 (state_after on the final xh)
   {
@@ -941,6 +1222,73 @@ int c2ray_b200_evolve3d(c2ray_ctx* c, double /*time*/, double dt, int32_t restar
   S.photon_loss_all = tail[0];
   S.sum_nbox_all = (int64_t)llround(tail[NumFreqBnd]);
   if (st) *st = S;
+  return C2RAY_OK;
+}
+
+int c2ray_b200_set_dump(c2ray_ctx* c, const char* dump_dir, double interval_s) {
+  if (!c) return fail(C2RAY_ERR_ARG, "null argument");
+  c->dump_dir = dump_dir ? dump_dir : "";
+  c->dump_interval_s = interval_s;
+  return C2RAY_OK;
+}
+
+int c2ray_b200_write_iteration_dump(c2ray_ctx* c, const char* path, int32_t niter) {
+  if (!c || !path) return fail(C2RAY_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  return write_iteration_dump_file(c, path, niter);
+}
+
+int c2ray_b200_read_iteration_dump(c2ray_ctx* c, const char* path, int32_t* niter) {
+  if (!c || !path) return fail(C2RAY_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  int ni = 0;
+  int rc = read_iteration_dump_file(c, path, &ni);
+  if (rc) return rc;
+  if (niter) *niter = ni;
+  return C2RAY_OK;
+}
+
+int c2ray_b200_write_stream2(c2ray_ctx* c, const char* results_dir, double zred_now) {
+  if (!c || !results_dir) return fail(C2RAY_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  if (c->rank != 0) return C2RAY_OK;  // output.F90:260 if (rank == 0)
+  const std::string z = c2io::f6_3(zred_now), dir = results_dir;
+  int rc;
+  if ((rc = write_plane_file(c, join_dir(dir, "xfrac3d_" + z + ".bin"), c->xh + c->N3, 8, false))) return rc;      // xh(:,:,:,1)
+  if ((rc = write_plane_file(c, join_dir(dir, "xfrac3dHe1_" + z + ".bin"), c->xhe + c->N3, 8, false))) return rc;  // xhe(:,:,:,1)
+  return write_plane_file(c, join_dir(dir, "xfrac3dHe2_" + z + ".bin"), c->xhe + 2 * c->N3, 8, false);             // xhe(:,:,:,2)
+}
+
+int c2ray_b200_write_stream3(c2ray_ctx* c, const char* results_dir, double zred_now) {
+  if (!c || !results_dir) return fail(C2RAY_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  if (c->rank != 0) return C2RAY_OK;  // output.F90:323
+  const std::string z = c2io::f6_3(zred_now), dir = results_dir;
+  int rc;
+  if (!c->par.isothermal &&
+      (rc = write_plane_file(c, join_dir(dir, "Temper3D_" + z + ".bin"), c->temp, 4, false))) return rc;  // real(temperature_grid(i,j,k,0))
+  if ((rc = write_plane_file(c, join_dir(dir, "IonRates3D_" + z + ".bin"), c->rates, 8, true))) return rc;  // real(phih_grid)
+  return write_plane_file(c, join_dir(dir, "HeatRates3D_" + z + ".bin"), c->rates + 3 * c->N3, 8, true);    // real(phiheat)
+}
+
+int c2ray_b200_fortran_records_write(const char* path, int32_t n, const void* const* data, const int64_t* bytes,
+                                     int64_t max_subrecord) {
+  if (!path || n < 0 || (n > 0 && (!data || !bytes))) return fail(C2RAY_ERR_ARG, "bad argument");
+  c2io::RecordWriter w(max_subrecord > 0 ? (uint64_t)max_subrecord : c2io::MAX_SUBRECORD);
+  if (!w.open(path)) return fail(C2RAY_ERR_STATE, std::string("cannot open ") + path + " for writing");
+  for (int i = 0; i < n; i++)
+    if (bytes[i] < 0 || !w.record(data[i], (uint64_t)bytes[i])) return fail(C2RAY_ERR_STATE, "short write");
+  if (!w.close()) return fail(C2RAY_ERR_STATE, "error closing file");
+  return C2RAY_OK;
+}
+
+int c2ray_b200_fortran_records_read(const char* path, int32_t n, void* const* data, const int64_t* bytes) {
+  if (!path || n < 0 || (n > 0 && (!data || !bytes))) return fail(C2RAY_ERR_ARG, "bad argument");
+  c2io::RecordReader r;
+  if (!r.open(path)) return fail(C2RAY_ERR_STATE, std::string("cannot open ") + path);
+  for (int i = 0; i < n; i++)
+    if (bytes[i] < 0 || !r.record(data[i], (uint64_t)bytes[i]))
+      return fail(C2RAY_ERR_STATE, "record " + std::to_string(i) + " does not have the expected length or the file is corrupt");
   return C2RAY_OK;
 }
 

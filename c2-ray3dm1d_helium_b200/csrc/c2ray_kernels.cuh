@@ -146,7 +146,7 @@ struct GridPtrs {
 __global__ void k_secion_factors(const double* __restrict__ xh_av, size_t N3, double* __restrict__ out) {
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N3) return;
-  const SecIon y = secion_factors(fmax(xh_av[p + N3], epsilon));  // i_state = ion%h_av(1), evolve_point.F90:123,257
+  const SecIon y = secion_factors_fast(fmax(xh_av[p + N3], epsilon));  // i_state = ion%h_av(1), evolve_point.F90:123,257
   out[p] = y.y1R0; out[p + N3] = y.y1R1; out[p + 2 * N3] = y.y1R2;
   out[p + 3 * N3] = y.y2R0; out[p + 4 * N3] = y.y2R1; out[p + 5 * N3] = y.y2R2;
 }
@@ -344,12 +344,14 @@ struct ChemTotals {
 };
 
 __global__ void __launch_bounds__(128)
-k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out) {
+k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out, size_t p_begin, size_t p_end) {
+  // cells [p_begin, p_end) of the mesh: the whole mesh on one rank, this rank's share when the pass is split over
+  // ranks (cells are independent, evolve.F90:477-484)
   const size_t N3 = P.N3;
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t p = p_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool iso = d_run.isothermal != 0;
   int vote = 0, nit = 0, nsub = 0;
-  if (p < N3) {
+  if (p < p_end) {
     Ion ion;
     // evolve_point.F90:368-378.  Only the live members are loaded: ion%h(1), ion%he(2) are
     // overwritten by doric before any use and ion%h_old(0), ion%he_old(0) are never read.
@@ -418,7 +420,8 @@ k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out)
 constexpr int CHEM_BURST = 32;  // thermal sub-steps per state-machine turn (8: 36 ms, 32: 30 ms on config 5 at 256^3)
 
 __global__ void __launch_bounds__(128, 3)
-k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out, unsigned long long* next_cell) {
+k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out, unsigned long long* next_cell,
+                size_t p_begin, size_t p_end) {
   const size_t N3 = P.N3;
   const bool iso = d_run.isothermal != 0;
   const unsigned lane = threadIdx.x & 31;
@@ -443,8 +446,8 @@ k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_ou
       if (lane == (unsigned)(__ffs(want) - 1)) base = atomicAdd(next_cell, (unsigned long long)__popc(want));
       base = __shfl_sync(0xffffffffu, base, __ffs(want) - 1);
       if (phase == IDLE && !exhausted) {
-        const unsigned long long idx = base + __popc(want & ((1u << lane) - 1));
-        if (idx >= N3) {
+        const unsigned long long idx = p_begin + base + __popc(want & ((1u << lane) - 1));
+        if (idx >= p_end) {
           exhausted = true;
         } else {
           p = (long long)idx;
@@ -530,6 +533,19 @@ k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_ou
     if (nsb) atomicAdd(&tot->nsub_total, (unsigned long long)nsb);
     atomicMax(&tot->nit_max, (int)nm);
   }
+}
+
+// Cross-rank combination of the global-pass counters when the pass is split over ranks: sums travel as FP64 (exact
+// below 2^53), the maximum as int32.
+__global__ void k_chem_pack(const ChemTotals* tot, double* sum4, int* max1) {
+  sum4[0] = (double)tot->conv_flag; sum4[1] = (double)tot->nit_total; sum4[2] = (double)tot->nsub_total;
+  sum4[3] = tot->last_coef_T;  // written by the rank that owns the last mesh cell only, 0 elsewhere
+  max1[0] = tot->nit_max;
+}
+__global__ void k_chem_unpack(ChemTotals* tot, const double* sum4, const int* max1) {
+  tot->conv_flag = (int)sum4[0]; tot->nit_total = (unsigned long long)sum4[1];
+  tot->nsub_total = (unsigned long long)sum4[2]; tot->last_coef_T = sum4[3];
+  tot->nit_max = max1[0];
 }
 
 // photonstatistics.f90:117-147 / :208-247 : sum_p ndens*x for 5 species

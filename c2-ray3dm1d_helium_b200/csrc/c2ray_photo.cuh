@@ -62,6 +62,25 @@ __device__ __forceinline__ SecIon secion_factors(double i_state) {
   return y;
 }
 
+// The same factors for the once-per-iteration full-grid pass (k_secion_factors): the six powers of i_state share one
+// logarithm and the general-purpose pow (~200 instructions, 9 of them per cell) becomes exp(p ln x) without slow paths.
+// i_state is in [epsilon, 1], so 1 - i_state^p is in [0, 1]; an exact 0 (fully ionised cell) must stay an exact 0.
+__device__ __forceinline__ double pow01(double base, double p) { return base > 0.0 ? fast_exp(p * fast_log(base)) : 0.0; }
+__device__ __forceinline__ SecIon secion_factors_fast(double i_state) {
+  SecIon y;
+  const double L = fast_log(i_state);
+  y.y1R0 = 0.3908 * pow01(1.0 - fast_exp(0.4092 * L), 1.7592);
+  y.y1R1 = 0.0554 * pow01(1.0 - fast_exp(0.4614 * L), 1.6660);
+  y.y1R2 = 1.0 * pow01(1.0 - fast_exp(0.2663 * L), 1.3163);
+  const double xeb01 = 1.0 - fast_exp(0.38 * L);
+  const double xeb2 = 1.0 - fast_exp(0.34 * L);
+  const double p02 = fast_exp(0.2 * L);
+  y.y2R0 = 0.6941 * p02 * xeb01 * xeb01;
+  y.y2R1 = 0.0984 * p02 * xeb01 * xeb01;
+  y.y2R2 = 3.9811 * fast_exp(0.4 * L) * xeb2 * xeb2;
+  return y;
+}
+
 struct PhotAcc {  // per-cell accumulators, still to be multiplied by 1/vol (except a_in, a_out)
   double a_in, a_out, a_HI, a_HeI, a_HeII, f_heat, f_ion_HI, f_ion_HeI;
 };

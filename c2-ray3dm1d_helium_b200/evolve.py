@@ -241,6 +241,26 @@ class C2Ray:
         capi.check(self.lib.c2ray_b200_state_sums(self.ctx, C.c_int32(which), _p(out)))
         return out
 
+    # -- iteration dumps, restart, output streams (evolve.F90:233-367, output.F90:249-379) ------------------------
+    def set_dump(self, dump_dir, interval_s=15.0 * 60.0):
+        """dump_dir: where evolve3D writes iterdump1/2.bin (when interval_s >= 0) and where restart=1|2|3 reads."""
+        capi.check(self.lib.c2ray_b200_set_dump(self.ctx, None if dump_dir is None else os.fsencode(dump_dir),
+                                                C.c_double(interval_s)))
+
+    def write_iteration_dump(self, path, niter):
+        capi.check(self.lib.c2ray_b200_write_iteration_dump(self.ctx, os.fsencode(path), C.c_int32(niter)))
+
+    def start_from_dump(self, path):
+        niter = C.c_int32()
+        capi.check(self.lib.c2ray_b200_read_iteration_dump(self.ctx, os.fsencode(path), C.byref(niter)))
+        return niter.value
+
+    def write_stream2(self, results_dir, zred_now):
+        capi.check(self.lib.c2ray_b200_write_stream2(self.ctx, os.fsencode(results_dir), C.c_double(zred_now)))
+
+    def write_stream3(self, results_dir, zred_now):
+        capi.check(self.lib.c2ray_b200_write_stream3(self.ctx, os.fsencode(results_dir), C.c_double(zred_now)))
+
     # -- parity hooks -----------------------------------------------------------------------------------------
     def photoion_rates(self, col6, vol, nflux3, i_state):
         col6 = _f64(col6).reshape(-1, 6)
@@ -308,6 +328,27 @@ class C2Ray:
         t = C.c_double()
         capi.check(self.lib.c2ray_b200_measure_fp64(self.ctx, C.byref(t)))
         return t.value
+
+
+def fortran_records_write(path, arrays, max_subrecord=0):
+    """Write numpy arrays as Fortran unformatted sequential records (one record each) through the library's record
+    layer -- no device needed."""
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    n = len(arrays)
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+    sizes = (C.c_int64 * n)(*[a.nbytes for a in arrays])
+    capi.check(capi.load().c2ray_b200_fortran_records_write(os.fsencode(path), C.c_int32(n), ptrs, sizes,
+                                                            C.c_int64(max_subrecord)))
+
+
+def fortran_records_read(path, specs):
+    """Read records of known (dtype, count) back: returns a list of 1-D arrays; raises on any length mismatch."""
+    arrays = [np.zeros(cnt, dtype=dt) for dt, cnt in specs]
+    n = len(arrays)
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+    sizes = (C.c_int64 * n)(*[a.nbytes for a in arrays])
+    capi.check(capi.load().c2ray_b200_fortran_records_read(os.fsencode(path), C.c_int32(n), ptrs, sizes))
+    return arrays
 
 
 def source_partition(NumSrc, rank, npr):

@@ -129,7 +129,11 @@ int c2ray_b200_snapshot_state(c2ray_ctx* ctx);
 int c2ray_b200_restore_state(c2ray_ctx* ctx);
 
 /* ---- the hot path ---------------------------------------------------------------------------------- */
-/* evolve.F90:78 evolve3D(time,dt,restart) on the device-resident state (restart must be 0). */
+/* evolve.F90:78 evolve3D(time,dt,restart) on the device-resident state.  restart = 0: a fresh time step;
+ * 1, 2, 3: resume the iteration from iterdump1.bin, iterdump2.bin, iterdump.bin in the dump directory (:137-141).
+ * With a communicator attached the global pass is split over the ranks (reduce-scatter of the rate grids, 1/npr of
+ * the cells per rank, all-gather of the fractions the next sweep reads) unless C2RAY_SPLIT_CHEM=0; results are those
+ * of the reference's allreduce + replicated pass. */
 int c2ray_b200_evolve3d(c2ray_ctx* ctx, double time, double dt, int32_t restart, c2ray_stats* stats);
 /* The drop-in for the Fortran evolve3D body: H2D of the module arrays, evolve3D, D2H of the results. */
 int c2ray_b200_evolve3d_host(c2ray_ctx* ctx, double time, double dt, int32_t restart, const double* ndens,
@@ -171,6 +175,30 @@ int c2ray_b200_rec_colion_batch(c2ray_ctx* ctx, int32_t n, const double* T, doub
  * coldenshe_out(:,:,:,0:1), Fortran layout): pos[n][3] unwrapped, srcpos[3]; out4[n][4] = cdensi, he0, he1, path */
 int c2ray_b200_cinterp_batch(c2ray_ctx* ctx, int32_t n, const int32_t* pos, const int32_t srcpos[3],
                              const double* coldensh_out, const double* coldenshe_out, double* out4);
+
+/* ---- iteration dumps, restart, output streams (Fortran form="unformatted" sequential files) --------- */
+/* evolve.F90:199-213: during evolve3d rank 0 writes <dump_dir>/iterdump1.bin and iterdump2.bin alternately whenever
+ * more than interval_s seconds have passed since the call started or the last dump (the reference: 15*60).
+ * interval_s < 0 disables the dumps.  dump_dir is also where evolve3d(restart=1|2|3) looks for iterdump1.bin |
+ * iterdump2.bin | iterdump.bin (evolve.F90:279 start_from_dump; every rank reads the file itself). */
+int c2ray_b200_set_dump(c2ray_ctx* ctx, const char* dump_dir, double interval_s);
+/* evolve.F90:233 write_iteration_dump(niter) to an explicit path: records niter, photon_loss_all(47), phih_grid,
+ * xh_av, xh_intermed, phihe_grid, xhe_av, xhe_intermed [, phiheat, temperature_grid(real(si))] */
+int c2ray_b200_write_iteration_dump(c2ray_ctx* ctx, const char* path, int32_t niter);
+/* evolve.F90:279 start_from_dump: loads the records above into the device-resident arrays, returns niter */
+int c2ray_b200_read_iteration_dump(c2ray_ctx* ctx, const char* path, int32_t* niter);
+/* output.F90:249 write_stream2: <results_dir>/xfrac3d_<z>.bin, xfrac3dHe1_<z>.bin, xfrac3dHe2_<z>.bin with
+ * <z> = trim(adjustl(f6.3 of zred_now)); each file: record mesh(1:3) int32, record N3 real(dp).  Rank 0 only. */
+int c2ray_b200_write_stream2(c2ray_ctx* ctx, const char* results_dir, double zred_now);
+/* output.F90:312 write_stream3: Temper3D_<z>.bin (temperature_grid(:,:,:,0), not when isothermal),
+ * IonRates3D_<z>.bin (real(phih_grid)), HeatRates3D_<z>.bin (real(phiheat)); N3 real(si) each.  Rank 0 only. */
+int c2ray_b200_write_stream3(c2ray_ctx* ctx, const char* results_dir, double zred_now);
+/* The record layer itself on host memory (no device, no context): n records data[i] of bytes[i] bytes.  Records
+ * above max_subrecord bytes (<= 0: the compilers' 2^31-9) are split into subrecords with signed markers as gfortran
+ * and ifort do.  read fails unless every record has exactly the expected length. */
+int c2ray_b200_fortran_records_write(const char* path, int32_t n, const void* const* data, const int64_t* bytes,
+                                     int64_t max_subrecord);
+int c2ray_b200_fortran_records_read(const char* path, int32_t n, void* const* data, const int64_t* bytes);
 
 /* ---- multi-GPU (mpi.F90 my_mpi: rank, npr ; evolve.F90:505-548 allreduce) ---------------------------- */
 /* 128-byte NCCL unique id created on rank 0 and broadcast by the host (MPI_BCAST / torch.distributed). */

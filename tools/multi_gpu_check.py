@@ -1,0 +1,101 @@
+"""Multi-GPU parity check, run under torchrun with N >= 2 ranks (one per GPU):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      tools/multi_gpu_check.py [mesh] [num_src] [steps]
+
+For each of two consecutive evolve3D time steps it compares
+  (a) the split global pass (reduce-scatter -> chemistry on N3/npr cells -> all-gather, the default with a communicator)
+      against the reference's scheme (allreduce of the rate grids + replicated pass, C2RAY_SPLIT_CHEM=0): bitwise at 2
+      ranks in deterministic mode (a+b is the only sum), 1e-12 otherwise;
+  (b) both against one rank tracing every source alone (tolerance: summation order of the rate grids);
+  (c) that every rank ends with the same full state and rate grids.
+Prints one line per rank and exits non-zero on a mismatch."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+import c2ray_b200
+
+
+def run(p, local, uid, rank, world, split, steps):
+    os.environ["C2RAY_SPLIT_CHEM"] = "1" if split else "0"
+    c = c2ray_b200.from_problem(p, device=local, deterministic=True)
+    if uid is not None:
+        c.comm_init(uid, rank, world)
+    hist = []
+    for s in range(steps):
+        st = c.evolve3D(0.0, p["dt"], 0)
+        hist.append((st["niter"], tuple(int(x) for x in st["conv_hist"]), st["sum_nbox_all"], st["photon_loss_all"],
+                     st["photcons"], st["ms_chem"], st["ms_allreduce"], st["ms_sweep"]))
+    out = c.get_state() + tuple(c.get_rates()) + tuple(c.get_work_state())
+    c.close()
+    return hist, out
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-300)))
+
+
+def main():
+    mesh = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    nsrc = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    p = c2ray_b200.synth.make_problem(2, n=mesh, num_src=nsrc, isothermal=False)
+
+    def uid():
+        u = [c2ray_b200.C2Ray.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(u, src=0)
+        return u[0]
+
+    h_split, s_split = run(p, local, uid(), rank, world, True, steps)
+    h_repl, s_repl = run(p, local, uid(), rank, world, False, steps)
+    h_one, s_one = run(p, local, None, 0, 1, False, steps)
+    ok = True
+    # integer histories: niter, conv_flag per iteration, sum_nbox
+    for a, b, c1 in zip(h_split, h_repl, h_one):
+        ok &= a[:3] == b[:3] == c1[:3]
+        ok &= abs(a[3] - c1[3]) <= 1e-10 * abs(c1[3]) + 1e-300 and abs(a[4] - c1[4]) <= 1e-9
+    tol_sr = 0.0 if world == 2 else 1e-12
+    e_sr = max(relerr(x, y) for x, y in zip(s_split, s_repl))
+    ok &= e_sr <= tol_sr
+    # against one rank: fractions 1e-8 rel + 2e-10 abs (tests/common.py), T one float ulp, rates 1e-8
+    names = ["xh", "xhe", "T", "phih", "phihe", "phiheat", "xh_av", "xhe_av", "xh_int", "xhe_int"]
+    errs = {}
+    for n, x, y in zip(names, s_split, s_one):
+        if n in ("xh", "xhe", "xh_av", "xhe_av", "xh_int", "xhe_int"):
+            errs[n] = float(np.max(np.abs(x - y) / (1e-8 * np.abs(y) + 2e-10)))
+        elif n == "T":
+            errs[n] = float(np.max(np.abs(x.astype(np.float64) - y) / (1.3e-7 * np.abs(y) + 1e-30)))
+        else:
+            errs[n] = float(np.max(np.abs(x - y) / (1e-8 * np.abs(y) + 1e-300)))
+    ok &= all(v < 1 for v in errs.values())
+    # every rank holds the same full result
+    mine = torch.tensor([float(np.sum(a.astype(np.float64))) for a in s_split], dtype=torch.float64, device="cuda")
+    lo, hi = mine.clone(), mine.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool(torch.equal(lo, hi))
+    ok &= same
+    ms = lambda h: (sum(x[7] for x in h), sum(x[5] for x in h), sum(x[6] for x in h))
+    print(f"rank {rank}/{world}: mesh {mesh} sources {nsrc} niter {[h[0] for h in h_split]} split-vs-replicated {e_sr:.2e} "
+          f"(tol {tol_sr:g}) vs-one-rank err/tol {max(errs.values()):.3f} all-ranks-equal {same} | ms sweep/chem/comm split "
+          f"{ms(h_split)[0]:.1f}/{ms(h_split)[1]:.1f}/{ms(h_split)[2]:.1f} replicated {ms(h_repl)[0]:.1f}/{ms(h_repl)[1]:.1f}/{ms(h_repl)[2]:.1f}"
+          f" -> {'OK' if ok else 'MISMATCH'}", flush=True)
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
