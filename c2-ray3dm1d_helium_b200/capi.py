@@ -24,7 +24,7 @@ EXPORTS = [
     "c2ray_b200_timer_start", "c2ray_b200_timer_stop",
     "c2ray_b200_set_dump", "c2ray_b200_write_iteration_dump", "c2ray_b200_read_iteration_dump",
     "c2ray_b200_write_stream2", "c2ray_b200_write_stream3", "c2ray_b200_fortran_records_write",
-    "c2ray_b200_fortran_records_read",
+    "c2ray_b200_fortran_records_read", "c2ray_b200_set_clumping_grid", "c2ray_b200_set_LLS",
 ]
 
 

@@ -137,6 +137,11 @@ struct c2ray_ctx {
   nccl_comm comm = nullptr;
   int split_chem = 1;          // env C2RAY_SPLIT_CHEM: evolve3d splits the global pass over the ranks (see split_active)
   double* d_chemred = nullptr; // 4 sums (FP64) + 1 maximum (int32) of the global-pass counters, for the cross-rank combination
+  // material: position-dependent clumping (type_of_clumping == 5) and Lyman-limit systems (use_LLS)
+  float* d_clump = nullptr;
+  float* d_lls = nullptr;
+  int lls_type = 0;
+  double coldensh_LLS = 0.0;
   // iteration dumps (evolve.F90:233-367) and output streams (output.F90:249-379)
   std::string dump_dir;
   double dump_interval_s = -1.0;  // < 0: no dumps; the reference writes one when 15 minutes have passed (:207)
@@ -328,7 +333,7 @@ int sweep_all(c2ray_ctx* c) {
       if (!c->d_secion) CK(cudaMalloc(&c->d_secion, 6 * c->N3 * sizeof(double)));
       LAUNCH(c, k_secion_factors, (unsigned)((c->N3 + 255) / 256), 256, c->xh_av, c->N3, c->d_secion);
     }
-    GridPtrs G{c->ndens, c->xh_av, c->xhe_av, c->rates, c->d_secion, c->N3};
+    GridPtrs G{c->ndens, c->xh_av, c->xhe_av, c->rates, c->d_secion, c->N3, c->lls_type, c->coldensh_LLS, c->d_lls};
     const int batch = c->par.deterministic ? 1 : c->slots_cap;
     ngroups = c->par.deterministic ? 1 : std::max(1, std::min(c->sweep_groups, std::min(batch, c->n_mine)));
     const int max_blocks = 148 * 16;
@@ -591,7 +596,7 @@ int global_pass_launch(c2ray_ctx* c, double dt, int* d_nit, size_t p_begin = 0, 
   if (rc) return rc;
   if (!c->par.isothermal && !c->have_cool) return fail(C2RAY_ERR_STATE, "cooling tables not set (c2ray_b200_set_cooling_tables)");
   CK(cudaMemsetAsync(c->d_chem, 0, sizeof(ChemTotals), c->stream));
-  ChemPtrs P{c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->temp, c->rates, c->N3};
+  ChemPtrs P{c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->temp, c->rates, c->N3, c->d_clump};
   // auto: the queue-driven kernel pays off once cells need many thermal sub-steps (divergence); measured break-even
   // between 10 and 40 sub-steps per cell (config 2: ~10, simple kernel faster; config 5: 42, queue 2x faster)
   const bool use_queue = c->chem_mode == 1 || (c->chem_mode < 0 && c->last_nsub_per_cell > 20.0);
@@ -711,7 +716,7 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   void* ptrs[] = {c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->rates, c->temp, c->snap_xh,
                   c->snap_xhe, c->snap_temp, c->d_srcpos, c->d_nf, c->d_nfpl, c->d_nfqpl, c->d_srcids, c->d_tb, c->d_cool,
-                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell, c->d_chemred};
+                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell, c->d_chemred, c->d_clump, c->d_lls};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
   for (int s = 0; s < 3; s++) if (c->packed[s]) cudaFree(c->packed[s]);
@@ -920,6 +925,34 @@ int c2ray_b200_set_geometry(c2ray_ctx* c, const double dr[3], double vol, double
   for (int d = 0; d < 3; d++) c->dr[d] = dr[d];
   c->vol = vol; c->zred = zred;
   c->run_dirty = true;
+  return C2RAY_OK;
+}
+
+int c2ray_b200_set_clumping_grid(c2ray_ctx* c, const float* clumping_grid) {
+  if (!c) return fail(C2RAY_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  if (!clumping_grid) {  // back to the scalar of c2ray_params (type_of_clumping 1-4)
+    if (c->d_clump) { CK(cudaFree(c->d_clump)); c->d_clump = nullptr; }
+    return C2RAY_OK;
+  }
+  if (!c->d_clump) CK(cudaMalloc(&c->d_clump, c->N3 * sizeof(float)));
+  CK(cudaMemcpy(c->d_clump, clumping_grid, c->N3 * sizeof(float), cudaMemcpyHostToDevice));
+  return C2RAY_OK;
+}
+
+int c2ray_b200_set_LLS(c2ray_ctx* c, int32_t type_of_LLS, double coldensh_LLS, const float* LLS_grid) {
+  if (!c) return fail(C2RAY_ERR_ARG, "null argument");
+  if (type_of_LLS < 0 || type_of_LLS > 2) return fail(C2RAY_ERR_ARG, "type_of_LLS must be 0 (none), 1 (one value) or 2 (LLS_grid)");
+  if (type_of_LLS == 2 && !LLS_grid) return fail(C2RAY_ERR_ARG, "type_of_LLS = 2 needs LLS_grid");
+  CK(cudaSetDevice(c->device));
+  if (type_of_LLS == 2) {
+    if (!c->d_lls) CK(cudaMalloc(&c->d_lls, c->N3 * sizeof(float)));
+    CK(cudaMemcpy(c->d_lls, LLS_grid, c->N3 * sizeof(float), cudaMemcpyHostToDevice));
+  } else if (c->d_lls) {
+    CK(cudaFree(c->d_lls)); c->d_lls = nullptr;
+  }
+  c->lls_type = type_of_LLS;
+  c->coldensh_LLS = type_of_LLS == 1 ? coldensh_LLS : 0.0;
   return C2RAY_OK;
 }
 
@@ -1199,7 +1232,7 @@ int c2ray_b200_evolve3d(c2ray_ctx* c, double /*time*/, double dt, int32_t restar
     // total_rates(dt, xh_av, xhe_av) with the coefficients the reference's module globals hold at this point
     const double coef_T = c->par.isothermal ? c->par.temper_val : cht.last_coef_T;
     CK(cudaMemsetAsync(c->d_sums, 0, 3 * sizeof(double), c->stream));
-    if (coef_T > 0.0) LAUNCH(c, k_total_rates, 148 * 4, 256, c->ndens, c->xh_av, c->xhe_av, c->N3, coef_T, c->d_sums);
+    if (coef_T > 0.0) LAUNCH(c, k_total_rates, 148 * 4, 256, c->ndens, c->xh_av, c->xhe_av, c->N3, coef_T, c->d_sums, c->d_clump);
     double t3[3];
     CK(cudaMemcpyAsync(t3, c->d_sums, sizeof(t3), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

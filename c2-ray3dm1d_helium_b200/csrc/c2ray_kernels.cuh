@@ -140,6 +140,11 @@ struct GridPtrs {
   double* rates;          // phih | phihe0 | phihe1 | phiheat, N3 each
   const double* secion;   // (N3,6) secondary-ionisation factors y1R(1:3), y2R(1:3) of every cell (non-isothermal)
   size_t N3;
+  // Lyman-limit systems (evolve_point.F90:170-180): type_of_LLS 0 none, 1 one column density per cell for the whole
+  // mesh, 2 LLS_grid(i,j,k) (material's real array)
+  int lls_type;
+  double coldensh_LLS;
+  const float* lls_grid;
 };
 
 // radiation_photoionrates.f90:557-565 for every cell: depends on xh_av(1) only, so once per iteration, not per source
@@ -277,6 +282,10 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
       const double xs = d_run.dr[0] * ddi, ys = d_run.dr[1] * ddj, zs = d_run.dr[2] * ddk;
       const double dist2 = xs * xs + ys * ys + zs * zs;
       vol_ph = FL(4.0f) * pi * dist2 * path;                // :168
+      if (G.lls_type) {                                      // :177-180 coldensh_in + coldensh_LLS * path/dr(1)
+        const double cl = G.lls_type == 2 ? (double)G.lls_grid[p] : G.coldensh_LLS;
+        cin_H = cin_H + __ddiv_rn(cl * path, d_run.dr[0]);
+      }
     }
     // evolve_point.F90:237-244
     const double cout_H = cin_H + h_av0 * ndens_p * path * (1.0 - abu_he);
@@ -333,6 +342,7 @@ struct ChemPtrs {
   float* temp;           // (N3,0:2) real(si)
   const double* rates;   // phih | phihe0 | phihe1 | phiheat
   size_t N3;
+  const float* clumping_grid;  // type_of_clumping == 5: material's clumping_grid(i,j,k); else nullptr
 };
 struct ChemTotals {
   int conv_flag;
@@ -376,7 +386,8 @@ k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out,
     RecCol rc;
     if (iso) ini_rec_colion_factors(d_run.temper_val, rc);  // mat_ini_test.F90:168
     double avg_temper = temp_av_old, temper1;
-    nit = do_chemistry(dt, n, ion, phiHI, phiHeI, phiHeII, heat, temper_old, avg_temper, temper1, rc, &nsub,
+    const double clumping = P.clumping_grid ? (double)P.clumping_grid[p] : d_run.clumping;  // evolve_point.F90:484
+    nit = do_chemistry(dt, n, ion, phiHI, phiHeI, phiHeII, heat, temper_old, avg_temper, temper1, rc, clumping, &nsub,
                        p == N3 - 1 ? &tot->last_coef_T : nullptr);
     double temp_av_new = temp_av_old;
     if (!iso) {  // set_temperature_point: stored as real(si), read back as such (:404)
@@ -433,7 +444,7 @@ k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_ou
   RecCol rc;
   ThermState TS;
   ChemIter it;
-  double n = 0, phiHI = 0, phiHeI = 0, phiHeII = 0, heat = 0, de = 0;
+  double n = 0, phiHI = 0, phiHeI = 0, phiHeII = 0, heat = 0, de = 0, clumping = d_run.clumping;
   double temper0 = 0, temper1 = 0, avg_temper = 0, temp_av_old = 0, yh0_old = 0, yhe0_old = 0, yhe2_old = 0;
   int nit = 0, votes = 0, nit_sum = 0, nit_max = 0, nsub = 0;
   if (iso) ini_rec_colion_factors(d_run.temper_val, rc);  // mat_ini_test.F90:168
@@ -464,6 +475,7 @@ k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_ou
           ion.he_av0 = fmax(epsilon, yhe0_old); ion.he_av1 = fmax(epsilon, P.xhe_av[p + N3]);
           ion.he_av2 = fmax(epsilon, yhe2_old);
           n = P.ndens[p];
+          if (P.clumping_grid) clumping = (double)P.clumping_grid[p];  // evolve_point.F90:484
           if (iso) { temp_av_old = d_run.temper_val; temper0 = d_run.temper_val; }
           else { temp_av_old = (double)P.temp[p + N3]; temper0 = (double)P.temp[p + 2 * N3]; }
           phiHI = P.rates[p]; phiHeI = P.rates[N3 + p]; phiHeII = P.rates[2 * N3 + p];
@@ -479,7 +491,7 @@ k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_ou
     if (phase == IONIZE) {
       nit++;
       if (!iso && (size_t)p == N3 - 1) tot->last_coef_T = avg_temper;
-      de = chem_ionization(dt, n, ion, phiHI, phiHeI, phiHeII, avg_temper, temper1, rc, it);
+      de = chem_ionization(dt, n, ion, phiHI, phiHeI, phiHeII, avg_temper, temper1, rc, it, clumping);
       temper1 = temper0;
       if (iso) {
         phase = TEST;
@@ -579,16 +591,18 @@ __global__ void k_state_sums(const double* __restrict__ ndens, const double* __r
 // He recombinations, summed over the mesh with the coefficients the module globals hold (coef_T, see ChemTotals).
 // out3 += (totrec, totcollisions, recomions) before the *vol*dt factor.
 __global__ void k_total_rates(const double* __restrict__ ndens, const double* __restrict__ xh_av,
-                              const double* __restrict__ xhe_av, size_t N3, double coef_T, double* out3) {
+                              const double* __restrict__ xhe_av, size_t N3, double coef_T, double* out3,
+                              const float* __restrict__ clumping_grid) {
   __shared__ RecCol rcs;
   __shared__ double sh[3][32];
   if (threadIdx.x == 0) ini_rec_colion_factors(coef_T, rcs);
   __syncthreads();
   const RecCol rc = rcs;
-  const double clumping = d_run.clumping;
+  double clumping = d_run.clumping;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N3; p += (size_t)gridDim.x * blockDim.x) {
     const double n = ndens[p];
+    if (clumping_grid) clumping = (double)clumping_grid[p];  // photonstatistics.f90:176
     const double h0 = xh_av[p], h1 = xh_av[p + N3], he0 = xhe_av[p], he1 = xhe_av[p + N3], he2 = xhe_av[p + 2 * N3];
     const double ne = electrondens(n, h1, he1, he2);
     s0 += n * (h1 * rc.brech0 * (1.0 - abu_he) + he1 * rc.breche0 * abu_he * 0.04) * ne * clumping;
@@ -641,7 +655,7 @@ __global__ void k_chemistry_batch(int n, double dt, const double* __restrict__ n
   if (d_run.isothermal) ini_rec_colion_factors(d_run.temper_val, rc);
   double avg = T3[3 * t + 1], t1;
   const int nit = do_chemistry(dt, ndens[t], ion, phi4[4 * t], phi4[4 * t + 1], phi4[4 * t + 2], phi4[4 * t + 3],
-                               T3[3 * t + 2], avg, t1, rc);
+                               T3[3 * t + 2], avg, t1, rc, d_run.clumping);
   T3[3 * t] = t1; T3[3 * t + 1] = avg;
   v[0] = ion.h0; v[1] = ion.h1; v[2] = ion.he0; v[3] = ion.he1; v[4] = ion.he2;
   v[5] = ion.h_av0; v[6] = ion.h_av1; v[7] = ion.he_av0; v[8] = ion.he_av1; v[9] = ion.he_av2;

@@ -360,9 +360,10 @@ struct ChemIter {  // values the convergence test of one iteration needs (:488-4
 // :488-597: coefficients at avg_temper, doric twice with the partial averaging; returns the electron density for thermal
 __device__ __forceinline__ double chem_ionization(double dt, double n, Ion& ion, double phiHI, double phiHeI,
                                                   double phiHeII, double avg_temper, double temper1, RecCol& rc,
-                                                  ChemIter& it) {
+                                                  ChemIter& it, double clumping) {
+  // clumping: material's module scalar, or clumping_grid(i,j,k) of the cell when type_of_clumping == 5
+  // (evolve_point.F90:484 clumping_point)
   const bool iso = d_run.isothermal != 0;
-  const double clumping = d_run.clumping;
   it.temper2 = temper1;
   it.yh0_av_old = ion.h_av0; it.yhe0_av_old = ion.he_av0; it.yhe2_av_old = ion.he_av2;
   double de = electrondens(n, ion.h_av1, ion.he_av1, ion.he_av2);
@@ -397,7 +398,8 @@ __device__ __forceinline__ bool chem_converged(const Ion& ion, const ChemIter& i
 // temper_old: T at the start of the step (grid(..,2)); avg_temper in: grid(..,1)
 __device__ __forceinline__ int do_chemistry(double dt, double n, Ion& ion, double phiHI, double phiHeI, double phiHeII,
                                             double heat, double temper_old, double& avg_temper, double& temper1_out,
-                                            RecCol& rc, int* nsub_total = nullptr, double* last_coef_T = nullptr) {
+                                            RecCol& rc, double clumping, int* nsub_total = nullptr,
+                                            double* last_coef_T = nullptr) {
   const bool iso = d_run.isothermal != 0;
   double temper1 = temper_old;
   const double temper0 = temper1;
@@ -406,7 +408,7 @@ __device__ __forceinline__ int do_chemistry(double dt, double n, Ion& ion, doubl
     nit++;
     ChemIter it;
     if (last_coef_T && !iso) *last_coef_T = avg_temper;  // what the reference's module globals hold afterwards
-    const double de = chem_ionization(dt, n, ion, phiHI, phiHeI, phiHeII, avg_temper, temper1, rc, it);
+    const double de = chem_ionization(dt, n, ion, phiHI, phiHeI, phiHeII, avg_temper, temper1, rc, it, clumping);
     temper1 = temper0;
     if (!iso) {
       const int ns = thermal(dt, temper1, avg_temper, de, n, ion, heat);

@@ -144,6 +144,18 @@ class C2Ray:
         dr = _f64(dr)
         capi.check(self.lib.c2ray_b200_set_geometry(self.ctx, _p(dr), C.c_double(vol), C.c_double(zred)))
 
+    def set_clumping_grid(self, clumping_grid):
+        """type_of_clumping == 5: material's clumping_grid(i,j,k) (real); None returns to the scalar clumping."""
+        g = None if clumping_grid is None else np.ascontiguousarray(clumping_grid, dtype=np.float32)
+        assert g is None or g.size == self.N3
+        capi.check(self.lib.c2ray_b200_set_clumping_grid(self.ctx, _p(g)))
+
+    def set_LLS(self, type_of_LLS, coldensh_LLS=0.0, LLS_grid=None):
+        """use_LLS: 0 off, 1 one column density per cell (coldensh_LLS), 2 position dependent (LLS_grid, real)."""
+        g = None if LLS_grid is None else np.ascontiguousarray(LLS_grid, dtype=np.float32)
+        assert g is None or g.size == self.N3
+        capi.check(self.lib.c2ray_b200_set_LLS(self.ctx, C.c_int32(type_of_LLS), C.c_double(coldensh_LLS), _p(g)))
+
     # -- material state -----------------------------------------------------------------------------------
     def set_state(self, ndens, xh, xhe, temperature_grid=None):
         a = [_f64(ndens), _f64(xh), _f64(xhe)]

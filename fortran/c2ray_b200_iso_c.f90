@@ -123,6 +123,41 @@ module c2ray_b200
        integer(c_int32_t), value :: rank, npr
        integer(c_int) :: rc
      end function c2ray_b200_comm_init
+     function c2ray_b200_set_dump(ctx, dump_dir, interval_s) bind(C, name="c2ray_b200_set_dump") result(rc)
+       import :: c_int, c_ptr, c_char, c_double
+       type(c_ptr), value :: ctx
+       character(kind=c_char), intent(in) :: dump_dir(*)   ! trim(adjustl(dump_dir))//c_null_char
+       real(c_double), value :: interval_s
+       integer(c_int) :: rc
+     end function c2ray_b200_set_dump
+     function c2ray_b200_set_clumping_grid(ctx, clumping_grid) bind(C, name="c2ray_b200_set_clumping_grid") result(rc)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       type(c_ptr), value :: clumping_grid                  ! c_loc(clumping_grid) (default real) or c_null_ptr
+       integer(c_int) :: rc
+     end function c2ray_b200_set_clumping_grid
+     function c2ray_b200_set_LLS(ctx, type_of_LLS, coldensh_LLS, LLS_grid) bind(C, name="c2ray_b200_set_LLS") result(rc)
+       import :: c_int, c_int32_t, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int32_t), value :: type_of_LLS
+       real(c_double), value :: coldensh_LLS
+       type(c_ptr), value :: LLS_grid                       ! c_loc(LLS_grid) (default real) or c_null_ptr
+       integer(c_int) :: rc
+     end function c2ray_b200_set_LLS
+     function c2ray_b200_write_stream2(ctx, results_dir, zred_now) bind(C, name="c2ray_b200_write_stream2") result(rc)
+       import :: c_int, c_ptr, c_char, c_double
+       type(c_ptr), value :: ctx
+       character(kind=c_char), intent(in) :: results_dir(*)
+       real(c_double), value :: zred_now
+       integer(c_int) :: rc
+     end function c2ray_b200_write_stream2
+     function c2ray_b200_write_stream3(ctx, results_dir, zred_now) bind(C, name="c2ray_b200_write_stream3") result(rc)
+       import :: c_int, c_ptr, c_char, c_double
+       type(c_ptr), value :: ctx
+       character(kind=c_char), intent(in) :: results_dir(*)
+       real(c_double), value :: zred_now
+       integer(c_int) :: rc
+     end function c2ray_b200_write_stream3
      function c2ray_b200_last_error() bind(C, name="c2ray_b200_last_error") result(msg)
        import :: c_ptr
        type(c_ptr) :: msg
@@ -162,6 +197,7 @@ contains
     use radiation_tables, only: bb_photo_thick_table, bb_photo_thin_table, bb_heat_thick_table, bb_heat_thin_table, &
          bb_FreqBnd_LowerLimit, bb_FreqBnd_UpperLimit
     use radiation_sed_parameters, only: S_star
+    use file_admin, only: dump_dir
 #ifdef QUASARS
     use radiation_tables, only: qpl_photo_thick_table, qpl_photo_thin_table, qpl_heat_thick_table, &
          qpl_heat_thin_table, qpl_FreqBnd_LowerLimit, qpl_FreqBnd_UpperLimit
@@ -218,6 +254,10 @@ contains
     call check(c2ray_b200_upload_tables(ctx, 2_c_int32_t, tab), "upload_tables(Q)")
 #endif
     ! (-DPL: same with the pl_* arrays and sed index 1)
+
+    ! iteration dumps every 15 minutes into dump_dir, as evolve.F90:199-213 does; evolve3D's restart flag then finds
+    ! iterdump1.bin / iterdump2.bin / iterdump.bin there (evolve.F90:279 start_from_dump)
+    call check(c2ray_b200_set_dump(ctx, trim(adjustl(dump_dir))//c_null_char, 15.0_c_double*60.0_c_double), "set_dump")
 
 #ifdef MPI
     if (npr > 1) then
@@ -279,6 +319,11 @@ contains
     type(c_ptr) :: pt
 
     call check(c2ray_b200_set_geometry(ctx, dr, vol, zred), "set_geometry")   ! dr, vol, zred change every step
+    ! material's set_clumping / set_LLS run once per redshift slice (C2Ray.F90): when type_of_clumping == 5 or use_LLS
+    ! the host passes the fresh arrays here, e.g.
+    !   call check(c2ray_b200_set_clumping_grid(ctx, c_loc(clumping_grid)), "set_clumping_grid")
+    !   call check(c2ray_b200_set_LLS(ctx, int(type_of_LLS,c_int32_t), coldensh_LLS, c_loc(LLS_grid)), "set_LLS")
+    ! (clumping_grid and LLS_grid are private to the material module: it needs two one-line accessor routines)
     pt = c_null_ptr
     if (.not.isothermal) pt = c_loc(temperature_grid)
     call check(c2ray_b200_evolve3d_host(ctx, time, dt, int(restart, c_int32_t), ndens, xh, xhe, pt, st), "evolve3d")

@@ -113,6 +113,15 @@ int c2ray_b200_set_sources(c2ray_ctx* ctx, int32_t NumSrc, const int32_t* srcpos
 /* grid: dr(3), vol (proper, change every step: cosmology.f90:159) ; cosmology: zred */
 int c2ray_b200_set_geometry(c2ray_ctx* ctx, const double dr[3], double vol, double zred);
 
+/* material, type_of_clumping == 5 (c2ray_parameters.f90:67): clumping_grid(N3) real, read per cell by do_chemistry
+ * (evolve_point.F90:484 clumping_point) and by total_rates (photonstatistics.f90:176).  NULL: back to the scalar
+ * c2ray_params.clumping. */
+int c2ray_b200_set_clumping_grid(c2ray_ctx* ctx, const float* clumping_grid);
+/* material, use_LLS (c2ray_parameters.f90:72-77): type_of_LLS 0 none | 1 coldensh_LLS for every cell | 2 LLS_grid(N3)
+ * real (already scaled to a column density per cell, mat_ini_test.F90:742-743).  evolve0D adds
+ * coldensh_LLS*path/dr(1) to the incoming HI column density of every cell but the source's (evolve_point.F90:177-180).
+ * The LLS_loss counter (:277) is not kept: the reference feeds it photo_in_HI, a member photoion_rates never sets. */
+int c2ray_b200_set_LLS(c2ray_ctx* ctx, int32_t type_of_LLS, double coldensh_LLS, const float* LLS_grid);
 /* material: ndens(N3), xh(N3,0:1), xhe(N3,0:2), temperature_grid(N3,0:2) real(si) (NULL when isothermal) */
 int c2ray_b200_set_state(c2ray_ctx* ctx, const double* ndens, const double* xh, const double* xhe,
                          const float* temperature_grid);

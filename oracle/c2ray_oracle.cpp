@@ -127,6 +127,12 @@ struct Ctx {
   bool isothermal = false;
   double temper_val = 1e4;
   float clumping = 1.0f;
+  // mat_ini_test.F90:37,43-45: position dependent clumping (type_of_clumping == 5) and Lyman-limit systems
+  // (use_LLS; type_of_LLS 1: one value, 2: LLS_grid).  Both arrays are default real.
+  std::vector<float> clumping_grid, LLS_grid;
+  bool use_clumping_grid = false;
+  int type_of_LLS = 0;
+  double coldensh_LLS = 0.0;
   double dr[3], vol;
   double zred = 9.0, H0 = 0, Omega0 = 0.27;
   bool cosmological = true;
@@ -929,6 +935,10 @@ void evolve0D(Worker& W, const int* rtpos, int ns) {
       double zs = G.dr[2] * (double)(float)(rtpos[2] - sp[2]);
       double dist2 = xs * xs + ys * ys + zs * zs;
       vol_ph = F(4.0f) * pi * dist2 * path;
+      if (G.type_of_LLS != 0) {  // evolve_point.F90:177-180 (LLS_point: coldensh_LLS = LLS_grid(i,j,k))
+        const double coldensh_LLS = G.type_of_LLS == 2 ? (double)G.LLS_grid[p] : G.coldensh_LLS;
+        coldensh_in = coldensh_in + coldensh_LLS * path / G.dr[0];
+      }
     }
     W.cdh[p] = coldensh_in + coldens(path, h_av0, ndens_p, (1.0 - abu_he));
     W.cdhe0[p] = coldenshe_in[0] + coldens(path, he_av0, ndens_p, abu_he);
@@ -1039,7 +1049,11 @@ inline void get_temperature_point(size_t p, double& temper_inter, double& av_tem
 
 // evolve_point.F90:444-646 do_chemistry (local=.false. branch)
 int do_chemistry(double dt, double ndens_p, IonStates& ion, const PhotRates& phi, double temper1_in,
-                 double& avg_temper, double& temper1_out, RecCol& rc, long* therm_sub = nullptr) {
+                 double& avg_temper, double& temper1_out, RecCol& rc, long* therm_sub = nullptr,
+                 double clumping = -1.0) {
+  // clumping: the material module's scalar, which :484 (clumping_point) overwrites with clumping_grid(i,j,k) when
+  // type_of_clumping == 5; passed in rather than stored so that cells can run on several threads
+  if (clumping < 0.0) clumping = (double)G.clumping;
   const double path = 1.0;
   double temper1 = temper1_in, temper0 = temper1, temper2;
   int nit = 0;
@@ -1053,7 +1067,7 @@ int do_chemistry(double dt, double ndens_p, IonStates& ion, const PhotRates& phi
     double coldenshe_cell[2] = {coldens(path, ion.he[0], ndens_p, abu_he), coldens(path, ion.he[1], ndens_p, abu_he)};
     double yfrac, zfrac, y2afrac, y2bfrac;
     prepare_doric_factors(coldensh_cell, coldenshe_cell, yfrac, zfrac, y2afrac, y2bfrac);
-    doric(dt, de, ndens_p, ion, phi, yfrac, zfrac, y2afrac, y2bfrac, rc, (double)G.clumping);
+    doric(dt, de, ndens_p, ion, phi, yfrac, zfrac, y2afrac, y2bfrac, rc, clumping);
     de = electrondens(ndens_p, ion.h_av, ion.he_av);
     coldensh_cell = coldens(path, ion.h[0], ndens_p, (1.0 - abu_he));
     coldenshe_cell[0] = coldens(path, ion.he[0], ndens_p, abu_he);
@@ -1061,7 +1075,7 @@ int do_chemistry(double dt, double ndens_p, IonStates& ion, const PhotRates& phi
     prepare_doric_factors(coldensh_cell, coldenshe_cell, yfrac, zfrac, y2afrac, y2bfrac);
     const double ionh0old = ion.h[0], ionh1old = ion.h[1], ionhe0old = ion.he[0], ionhe1old = ion.he[1],
                  ionhe2old = ion.he[2], oldhav = ion.h_av[0], oldhe0av = ion.he_av[0], oldhe1av = ion.he_av[1];
-    doric(dt, de, ndens_p, ion, phi, yfrac, zfrac, y2afrac, y2bfrac, rc, (double)G.clumping);
+    doric(dt, de, ndens_p, ion, phi, yfrac, zfrac, y2afrac, y2bfrac, rc, clumping);
     ion.h[0] = (ion.h[0] + ionh0old) / 2.0;
     ion.h[1] = (ion.h[1] + ionh1old) / 2.0;
     ion.he[0] = (ion.he[0] + ionhe0old) / 2.0;
@@ -1115,7 +1129,8 @@ int evolve0D_global(double dt, size_t p, int& conv_flag, long* therm_sub) {
   if (!G.isothermal) phi.heat = G.phiheat[p];
   // do_chemistry :479-481: (temper_inter, avg_temper, temper1) = get_temperature_point
   double avg_temper = temp_av_old, temper1;
-  int nit = do_chemistry(dt, ndens_p, ion, phi, temper_old, avg_temper, temper1, G.rc, therm_sub);
+  const double clumping = G.use_clumping_grid ? (double)G.clumping_grid[p] : (double)G.clumping;
+  int nit = do_chemistry(dt, ndens_p, ion, phi, temper_old, avg_temper, temper1, G.rc, therm_sub, clumping);
   if (!G.isothermal) {  // set_temperature_point :644
     G.temperature_grid[p] = (float)temper1;
     G.temperature_grid[p + N3] = (float)avg_temper;
@@ -1297,6 +1312,8 @@ void orc_photoion_rates_batch(int n, const double* col6, const double* vol, cons
 void orc_grid_init(const int* mesh, const double* dr, double vol) {
   for (int d = 0; d < 3; d++) { G.mesh[d] = mesh[d]; G.dr[d] = dr[d]; }
   G.vol = vol;
+  G.use_clumping_grid = false; G.clumping_grid.clear();
+  G.type_of_LLS = 0; G.coldensh_LLS = 0.0; G.LLS_grid.clear();
   const size_t N3 = ncell();
   G.ndens.assign(N3, 0); G.xh.assign(2 * N3, 0); G.xhe.assign(3 * N3, 0);
   G.xh_av.assign(2 * N3, 0); G.xhe_av.assign(3 * N3, 0); G.xh_intermed.assign(2 * N3, 0); G.xhe_intermed.assign(3 * N3, 0);
@@ -1305,6 +1322,17 @@ void orc_grid_init(const int* mesh, const double* dr, double vol) {
   workers.clear();
 }
 void orc_set_geometry(const double* dr, double vol) { for (int d = 0; d < 3; d++) G.dr[d] = dr[d]; G.vol = vol; }
+// type_of_clumping == 5: clumping_grid (NULL switches back to the scalar)
+void orc_set_clumping_grid(const float* grid) {
+  G.use_clumping_grid = grid != nullptr;
+  if (grid) G.clumping_grid.assign(grid, grid + ncell()); else G.clumping_grid.clear();
+}
+// use_LLS: type 0 off, 1 coldensh_LLS for every cell, 2 LLS_grid
+void orc_set_LLS(int type_of_LLS, double coldensh_LLS, const float* grid) {
+  G.type_of_LLS = type_of_LLS;
+  G.coldensh_LLS = type_of_LLS == 1 ? coldensh_LLS : 0.0;
+  if (type_of_LLS == 2 && grid) G.LLS_grid.assign(grid, grid + ncell()); else G.LLS_grid.clear();
+}
 void orc_set_state(const double* ndens, const double* xh, const double* xhe, const float* temperature_grid) {
   const size_t N3 = ncell();
   memcpy(G.ndens.data(), ndens, N3 * 8); memcpy(G.xh.data(), xh, 2 * N3 * 8); memcpy(G.xhe.data(), xhe, 3 * N3 * 8);
@@ -1435,7 +1463,8 @@ int orc_global_pass(double dt, int nthreads, int* nit_out) {
         if (!G.isothermal) phi.heat = G.phiheat[p];
         double avg_temper = temp_av_old, temper1;
         rc_local = G.rc;
-        nit = do_chemistry(dt, G.ndens[p], ion, phi, temper_old, avg_temper, temper1, rc_local, &ts);
+        nit = do_chemistry(dt, G.ndens[p], ion, phi, temper_old, avg_temper, temper1, rc_local, &ts,
+                           G.use_clumping_grid ? (double)G.clumping_grid[p] : (double)G.clumping);
         if (!G.isothermal) { G.temperature_grid[p] = (float)temper1; G.temperature_grid[p + N3] = (float)avg_temper; }
         const double yh0 = G.xh_av[p], yhe0 = G.xhe_av[p], yhe2 = G.xhe_av[p + 2 * N3];
         double temp_av_new, d1, d2;
@@ -1502,8 +1531,9 @@ void orc_state_sums(const double* xh, const double* xhe, double* out5) {
 void orc_total_rates(double dt, const double* xh_l, const double* xhe_l, double* out3) {
   const size_t N3 = ncell();
   double totrec = 0.0, totcollisions = 0.0, recomions = 0.0;
-  const double clumping = (double)G.clumping;
+  double clumping = (double)G.clumping;
   for (size_t p = 0; p < N3; p++) {
+    if (G.use_clumping_grid) clumping = (double)G.clumping_grid[p];  // photonstatistics.f90:176
     const double yh[2] = {xh_l[p], xh_l[p + N3]};
     const double yhe[3] = {xhe_l[p], xhe_l[p + N3], xhe_l[p + 2 * N3]};
     const double ndens_p = G.ndens[p];

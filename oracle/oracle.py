@@ -164,6 +164,14 @@ class Grid:
         t = None if temperature_grid is None else np.ascontiguousarray(temperature_grid, dtype=np.float32)
         lib().orc_set_state(*[x.ctypes.data_as(C.c_void_p) for x in a], None if t is None else t.ctypes.data_as(C.c_void_p))
 
+    def set_clumping_grid(self, grid):
+        g = None if grid is None else np.ascontiguousarray(grid, dtype=np.float32)
+        lib().orc_set_clumping_grid(None if g is None else g.ctypes.data_as(C.c_void_p))
+
+    def set_LLS(self, type_of_LLS, coldensh_LLS=0.0, LLS_grid=None):
+        g = None if LLS_grid is None else np.ascontiguousarray(LLS_grid, dtype=np.float32)
+        lib().orc_set_LLS(C.c_int(type_of_LLS), C.c_double(coldensh_LLS), None if g is None else g.ctypes.data_as(C.c_void_p))
+
     def set_work_state(self, xh_av, xhe_av, xh_intermed, xhe_intermed):
         a = [np.ascontiguousarray(x, dtype=np.float64) for x in (xh_av, xhe_av, xh_intermed, xhe_intermed)]
         lib().orc_set_work_state(*[x.ctypes.data_as(C.c_void_p) for x in a])
