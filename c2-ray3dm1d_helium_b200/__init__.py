@@ -6,5 +6,5 @@ Layout: csrc/ (CUDA kernels + C ABI), capi.py (ctypes binding), evolve.py (mirro
 evolve_source / radiation_* / doric interfaces), synth.py (synthetic inputs of the BASELINE configs).
 """
 from . import capi, synth  # noqa: F401
-from .evolve import (C2Ray, C2RayParameters, fortran_records_read, fortran_records_write, from_problem,  # noqa: F401
+from .evolve import (C2Ray, C2RayParameters, balanced_partition, fortran_records_read, fortran_records_write, from_problem,  # noqa: F401
                      read_cooling_tables, source_partition)

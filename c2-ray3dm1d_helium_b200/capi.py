@@ -25,6 +25,7 @@ EXPORTS = [
     "c2ray_b200_set_dump", "c2ray_b200_write_iteration_dump", "c2ray_b200_read_iteration_dump",
     "c2ray_b200_write_stream2", "c2ray_b200_write_stream3", "c2ray_b200_fortran_records_write",
     "c2ray_b200_fortran_records_read", "c2ray_b200_set_clumping_grid", "c2ray_b200_set_LLS",
+    "c2ray_b200_set_source_schedule", "c2ray_b200_balanced_partition", "c2ray_b200_my_sources",
 ]
 
 

@@ -35,6 +35,12 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
                                       std::to_string(__LINE__) + ")");                                   \
   } while (0)
 
+#define NC_(call)                                                                              \
+  do {                                                                                         \
+    int r_ = (call);                                                                           \
+    if (r_ != 0) return fail(C2RAY_ERR_NCCL, std::string(#call) + " failed: " + std::to_string(r_)); \
+  } while (0)
+
 // ---- NCCL through dlopen (no link-time dependency; torch's bundled libnccl is reused when already loaded) ----
 typedef struct { char internal[128]; } nccl_uid;
 typedef void* nccl_comm;
@@ -96,7 +102,6 @@ struct c2ray_ctx {
   int NumSrc = 0;
   int* d_srcpos = nullptr;
   double *d_nf = nullptr, *d_nfpl = nullptr, *d_nfqpl = nullptr;
-  int* d_srcids = nullptr;  // 0-based ids of this rank's sources, in source order
   int n_mine = 0;
   bool have_pl_flux = false, have_qpl_flux = false;
   double sum_nf[3] = {0, 0, 0};  // sum(NormFlux), sum(NormFluxPL), sum(NormFluxQPL) in source order
@@ -135,6 +140,13 @@ struct c2ray_ctx {
   // multi-GPU
   int rank = 0, npr = 1;
   nccl_comm comm = nullptr;
+  int schedule = 0;            // 0: do_grid_static round robin (master_slave.F90:85); 1: balanced by last pass's cost
+  int* d_nbox_all = nullptr;   // sub-box count per source of the last pass (this rank's sources; summed over ranks)
+  std::vector<int> my_ids;     // 0-based ids of this rank's sources
+  std::vector<char> src_pl, src_qpl;  // per source: NormFluxPL > 0, NormFluxQPL > 0
+  int* d_srcids_run = nullptr; // this rank's sources ordered for the sweep: black-body-only sources first
+  int n_single = 0;            // how many of them take the single-SED kernel
+  int run_key = -1;            // what d_srcids_run was built for (table presence bits); -1: rebuild
   int split_chem = 1;          // env C2RAY_SPLIT_CHEM: evolve3d splits the global pass over the ranks (see split_active)
   double* d_chemred = nullptr; // 4 sums (FP64) + 1 maximum (int32) of the global-pass counters, for the cross-rank combination
   // material: position-dependent clumping (type_of_clumping == 5) and Lyman-limit systems (use_LLS)
@@ -282,16 +294,65 @@ int alloc_sweep(c2ray_ctx* c, int want_slots) {
   return 0;
 }
 
-int rebuild_my_sources(c2ray_ctx* c) {
-  if (c->d_srcids) { cudaFree(c->d_srcids); c->d_srcids = nullptr; }
-  std::vector<int> ids;
-  for (int ns1 = 1 + c->rank; ns1 <= c->NumSrc; ns1 += c->npr) ids.push_back(ns1 - 1);  // master_slave.F90:85
-  c->n_mine = (int)ids.size();
-  if (c->n_mine) {
-    CK(cudaMalloc(&c->d_srcids, sizeof(int) * ids.size()));
-    CK(cudaMemcpy(c->d_srcids, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice));
-  }
+int upload_my_sources(c2ray_ctx* c) {
+  c->n_mine = (int)c->my_ids.size();
+  c->run_key = -1;  // sweep_all rebuilds and uploads the run-ordered list
   return 0;
+}
+
+int rebuild_my_sources(c2ray_ctx* c) {
+  c->my_ids.clear();
+  for (int ns1 = 1 + c->rank; ns1 <= c->NumSrc; ns1 += c->npr) c->my_ids.push_back(ns1 - 1);  // master_slave.F90:85
+  if (c->d_nbox_all) { cudaFree(c->d_nbox_all); c->d_nbox_all = nullptr; }
+  if (c->NumSrc > 0) {
+    CK(cudaMalloc(&c->d_nbox_all, sizeof(int) * c->NumSrc));
+    CK(cudaMemset(c->d_nbox_all, 0, sizeof(int) * c->NumSrc));
+  }
+  return upload_my_sources(c);
+}
+
+// Longest-processing-time-first assignment of sources to ranks: sources in order of decreasing cost (ties: lower
+// source number first) each go to the rank with the smallest load so far (ties: lowest rank).  Every rank computes the
+// same table from the same costs.  This is the static stand-in for the reference's master/slave hand-out
+// (master_slave.F90:124-326), where a free slave asks the master for the next source.
+void balanced_partition(int NumSrc, const long long* cost, int npr, int* owner) {
+  std::vector<int> order(NumSrc);
+  for (int i = 0; i < NumSrc; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  std::vector<long long> load(npr, 0);
+  for (int i : order) {
+    int best = 0;
+    for (int r = 1; r < npr; r++) if (load[r] < load[best]) best = r;
+    owner[i] = best;
+    load[best] += cost[i] > 0 ? cost[i] : 1;
+  }
+}
+
+// cells a source with `nbox` sub-boxes traces: prod_d (last_r - last_l + 1), evolve_source.F90:143-144
+long long source_cost(const c2ray_ctx* c, int nbox) {
+  long long cells = 1;
+  for (int d = 0; d < 3; d++) {
+    const long long reach = (long long)c->par.subboxsize * std::max(nbox, 1);
+    cells *= std::min<long long>(reach, c->geom.L[d]) + std::min<long long>(reach, c->geom.R[d]) + 1;
+  }
+  return cells;
+}
+
+// After a pass: share the sub-box counts and re-deal the sources for the next pass (balanced schedule only).
+int rebalance_sources(c2ray_ctx* c) {
+  if (c->schedule != 1 || !c->comm || c->npr <= 1 || c->NumSrc <= 0) return 0;
+  NC_(g_nccl.AllReduce(c->d_nbox_all, c->d_nbox_all, (size_t)c->NumSrc, NCCL_INT32, NCCL_SUM, c->comm, c->stream));
+  std::vector<int> nbox(c->NumSrc);
+  CK(cudaMemcpyAsync(nbox.data(), c->d_nbox_all, sizeof(int) * c->NumSrc, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemsetAsync(c->d_nbox_all, 0, sizeof(int) * c->NumSrc, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  std::vector<long long> cost(c->NumSrc);
+  for (int i = 0; i < c->NumSrc; i++) cost[i] = source_cost(c, nbox[i]);
+  std::vector<int> owner(c->NumSrc);
+  balanced_partition(c->NumSrc, cost.data(), c->npr, owner.data());
+  c->my_ids.clear();
+  for (int i = 0; i < c->NumSrc; i++) if (owner[i] == c->rank) c->my_ids.push_back(i);
+  return upload_my_sources(c);
 }
 
 // Sums the per-group totals into the context's aggregate and packs [photon_loss(1:47) | sum_nbox] behind the rate
@@ -337,27 +398,55 @@ int sweep_all(c2ray_ctx* c) {
     const int batch = c->par.deterministic ? 1 : c->slots_cap;
     ngroups = c->par.deterministic ? 1 : std::max(1, std::min(c->sweep_groups, std::min(batch, c->n_mine)));
     const int max_blocks = 148 * 16;
-    const bool multi_sed = c->tab[1][0] != nullptr || c->tab[2][0] != nullptr;  // PL / QPL tables present
+    // A source whose PL and QPL fluxes are zero (or whose tables are absent) contributes through the black-body
+    // tables only and takes the single-SED kernel, whatever other sources need: in a -DQUASARS run with QPL flux
+    // on a few bright sources the rest do not pay for the three-SED loop.  The list is ordered single-SED sources
+    // first; deterministic mode keeps source order and picks the kernel per source.
+    const bool has_bb = c->tab[0][0] != nullptr, has_pl = c->tab[1][0] != nullptr, has_qpl = c->tab[2][0] != nullptr;
+    auto is_multi = [&](int id) { return !has_bb || (has_pl && c->src_pl[id]) || (has_qpl && c->src_qpl[id]); };
+    const int key = (has_bb ? 1 : 0) | (has_pl ? 2 : 0) | (has_qpl ? 4 : 0) | (c->par.deterministic ? 8 : 0);
+    if (c->run_key != key) {
+      std::vector<int> order;
+      order.reserve(c->n_mine);
+      if (c->par.deterministic) {
+        order = c->my_ids;
+        c->n_single = 0;
+      } else {
+        for (int id : c->my_ids) if (!is_multi(id)) order.push_back(id);
+        c->n_single = (int)order.size();
+        for (int id : c->my_ids) if (is_multi(id)) order.push_back(id);
+      }
+      if (c->d_srcids_run) { cudaFree(c->d_srcids_run); c->d_srcids_run = nullptr; }
+      CK(cudaMalloc(&c->d_srcids_run, sizeof(int) * order.size()));
+      CK(cudaMemcpy(c->d_srcids_run, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));
+      c->run_key = key;
+    }
     const size_t slot_stride = (size_t)6 * g.cap;
     CK(cudaMemsetAsync(c->d_gtot, 0, sizeof(SweepTotals) * MAX_SWEEP_GROUPS, c->stream));
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for (int q = 0; q < ngroups; q++) CK(cudaStreamWaitEvent(c->gstream[q], c->ev_fork, 0));
-    for (int first = 0; first < c->n_mine; first += batch) {
-      const int ns = std::min(batch, c->n_mine - first);
+    for (int first = 0; first < c->n_mine;) {
+      // a batch never mixes the two kinds
+      bool multi_sed;
+      int ns;
+      if (c->par.deterministic) { multi_sed = is_multi(c->my_ids[first]); ns = 1; }
+      else if (first < c->n_single) { multi_sed = false; ns = std::min(batch, c->n_single - first); }
+      else { multi_sed = true; ns = std::min(batch, c->n_mine - first); }
+      struct Advance { int& f; int n; ~Advance() { f += n; } } advance{first, ns};
       const int per = (ns + ngroups - 1) / ngroups;
       int goff[MAX_SWEEP_GROUPS], gns[MAX_SWEEP_GROUPS];
       for (int q = 0; q < ngroups; q++) { goff[q] = std::min(q * per, ns); gns[q] = std::min(per, ns - goff[q]); }
       for (int q = 0; q < ngroups; q++)
         if (gns[q] > 0)
           LAUNCH_S(c, c->gstream[q], k_slots_init, (gns[q] + 127) / 128, 128, c->d_slots + goff[q], gns[q],
-                   c->d_srcids + first + goff[q], c->d_srcpos, c->d_nf, c->have_pl_flux ? c->d_nfpl : nullptr,
+                   c->d_srcids_run + first + goff[q], c->d_srcpos, c->d_nf, c->have_pl_flux ? c->d_nfpl : nullptr,
                    c->have_qpl_flux ? c->d_nfqpl : nullptr, c->d_gtot + q, c->d_active + goff[q]);
       const int reach3 = std::min(g.R[2], g.L[2]);
       int nact[MAX_SWEEP_GROUPS];
       for (int q = 0; q < ngroups; q++) nact[q] = gns[q];
       for (int b = 1;; b++) {
         for (int q = 0; q < ngroups; q++)
-          if (nact[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q]);
+          if (nact[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q], c->d_nbox_all);
         if (b > 1) {
           // From the second sub-box on most sources have dropped out (photon loss below 1e-10 of the flux): fetch the
           // number still active so that the shells of a level nobody traces are not launched at all and the grids
@@ -387,7 +476,7 @@ int sweep_all(c2ray_ctx* c) {
         if ((long long)g.subboxsize * b >= reach3) break;  // the do-while's extent test fails for every source
       }
       for (int q = 0; q < ngroups; q++)  // close the sources still active
-        if (nact[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q]);
+        if (nact[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q], c->d_nbox_all);
     }
     for (int q = 0; q < ngroups; q++) {
       CK(cudaEventRecord(c->ev_join[q], c->gstream[q]));
@@ -715,8 +804,8 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   void* ptrs[] = {c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->rates, c->temp, c->snap_xh,
-                  c->snap_xhe, c->snap_temp, c->d_srcpos, c->d_nf, c->d_nfpl, c->d_nfqpl, c->d_srcids, c->d_tb, c->d_cool,
-                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell, c->d_chemred, c->d_clump, c->d_lls};
+                  c->snap_xhe, c->snap_temp, c->d_srcpos, c->d_nf, c->d_nfpl, c->d_nfqpl, c->d_tb, c->d_cool,
+                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell, c->d_chemred, c->d_clump, c->d_lls, c->d_nbox_all, c->d_srcids_run};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
   for (int s = 0; s < 3; s++) if (c->packed[s]) cudaFree(c->packed[s]);
@@ -904,10 +993,11 @@ int c2ray_b200_set_sources(c2ray_ctx* c, int32_t NumSrc, const int32_t* srcpos, 
   c->NumSrc = NumSrc;
   c->have_pl_flux = nfpl != nullptr; c->have_qpl_flux = nfqpl != nullptr;
   c->sum_nf[0] = c->sum_nf[1] = c->sum_nf[2] = 0.0;
+  c->src_pl.assign(NumSrc, 0); c->src_qpl.assign(NumSrc, 0);
   for (int i = 0; i < NumSrc; i++) {
     c->sum_nf[0] += nf[i];
-    if (nfpl) c->sum_nf[1] += nfpl[i];
-    if (nfqpl) c->sum_nf[2] += nfqpl[i];
+    if (nfpl) { c->sum_nf[1] += nfpl[i]; c->src_pl[i] = nfpl[i] > 0.0; }
+    if (nfqpl) { c->sum_nf[2] += nfqpl[i]; c->src_qpl[i] = nfqpl[i] > 0.0; }
   }
   if (NumSrc > 0) {
     CK(cudaMalloc(&c->d_srcpos, sizeof(int) * 3 * NumSrc));
@@ -1076,6 +1166,7 @@ int c2ray_b200_pass_all_sources(c2ray_ctx* c, double /*dt*/, int32_t /*niter*/, 
   rc = allreduce_rates(c);
   if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));
+  if ((rc = rebalance_sources(c))) return rc;
   if (rt_updates) *rt_updates = (int64_t)t.updates;
   return C2RAY_OK;
 }
@@ -1083,19 +1174,20 @@ int c2ray_b200_pass_all_sources(c2ray_ctx* c, double /*dt*/, int32_t /*niter*/, 
 int c2ray_b200_do_source(c2ray_ctx* c, double /*dt*/, int32_t ns1, int32_t /*niter*/, int32_t* nbox, double* loss) {
   if (!c || ns1 < 1 || ns1 > c->NumSrc) return fail(C2RAY_ERR_ARG, "bad source number");
   // temporarily trace just this source
-  int* saved = c->d_srcids; const int saved_n = c->n_mine;
-  int id = ns1 - 1; int* d_id = nullptr;
   CK(cudaSetDevice(c->device));
-  CK(cudaMalloc(&d_id, sizeof(int)));
-  CK(cudaMemcpy(d_id, &id, sizeof(int), cudaMemcpyHostToDevice));
-  c->d_srcids = d_id; c->n_mine = 1;
+  std::vector<int> saved;
+  saved.swap(c->my_ids);
+  const int saved_n = c->n_mine;
+  c->my_ids.assign(1, ns1 - 1); c->n_mine = 1; c->run_key = -1;
   int rc = sweep_all(c);
-  c->d_srcids = saved; c->n_mine = saved_n;
-  if (rc) { cudaFree(d_id); return rc; }
   SweepTotals t;
-  CK(cudaMemcpyAsync(&t, c->d_tot, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  cudaFree(d_id);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(&t, c->d_tot, sizeof(t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = fail(C2RAY_ERR_CUDA, std::string("do_source: ") + cudaGetErrorString(e));
+  }
+  c->my_ids.swap(saved); c->n_mine = saved_n; c->run_key = -1;
+  if (rc) return rc;
   if (nbox) *nbox = (int)t.sum_nbox;
   if (loss) *loss = t.photon_loss;
   return C2RAY_OK;
@@ -1191,6 +1283,7 @@ int c2ray_b200_evolve3d(c2ray_ctx* c, double /*time*/, double dt, int32_t restar
     if (c->NumSrc > 0) {
       if (split) rc = reduce_scatter_rates(c); else rc = allreduce_rates(c);
       if (rc) return rc;
+      if ((rc = rebalance_sources(c))) return rc;  // balanced schedule: re-deal the sources for the next pass
       // evolve.F90:199-213: rank 0 writes an iteration dump when more than the interval (15 minutes) has passed
       if (c->dump_interval_s >= 0.0 && !c->dump_dir.empty()) {
         int due = 0;
@@ -1439,6 +1532,29 @@ int c2ray_b200_set_rank(c2ray_ctx* c, int32_t rank, int32_t npr) {
   CK(cudaSetDevice(c->device));
   c->rank = rank; c->npr = npr;
   return rebuild_my_sources(c);
+}
+
+int c2ray_b200_set_source_schedule(c2ray_ctx* c, int32_t mode) {
+  if (!c || mode < 0 || mode > 1) return fail(C2RAY_ERR_ARG, "schedule must be 0 (static round robin) or 1 (balanced)");
+  c->schedule = mode;
+  CK(cudaSetDevice(c->device));
+  return rebuild_my_sources(c);  // both schedules start from the round-robin deal
+}
+
+int c2ray_b200_balanced_partition(int32_t NumSrc, const int64_t* cost, int32_t npr, int32_t* owner) {
+  if (NumSrc < 0 || npr < 1 || (NumSrc > 0 && (!cost || !owner))) return fail(C2RAY_ERR_ARG, "bad argument");
+  std::vector<long long> cst(cost, cost + NumSrc);
+  std::vector<int> own(NumSrc);
+  balanced_partition(NumSrc, cst.data(), npr, own.data());
+  for (int i = 0; i < NumSrc; i++) owner[i] = own[i];
+  return C2RAY_OK;
+}
+
+int c2ray_b200_my_sources(c2ray_ctx* c, int32_t* ids, int32_t cap, int32_t* n) {
+  if (!c || !n) return fail(C2RAY_ERR_ARG, "null argument");
+  *n = (int32_t)c->my_ids.size();
+  if (ids) for (int i = 0; i < *n && i < cap; i++) ids[i] = c->my_ids[i] + 1;
+  return C2RAY_OK;
 }
 
 int c2ray_b200_rates_device_buffer(c2ray_ctx* c, void** dptr, int64_t* count) {

@@ -107,7 +107,7 @@ __global__ void k_slots_init(Slot* slots, int nslots, const int* __restrict__ sr
 
 // The `do while` test of evolve_source.F90:136-144 for every slot, then compaction of the active slots.
 // Single block.
-__global__ void k_decide(Slot* slots, int nslots, SweepGeom g, SweepTotals* tot, int* active_list) {
+__global__ void k_decide(Slot* slots, int nslots, SweepGeom g, SweepTotals* tot, int* active_list, int* nbox_all) {
   __shared__ int cnt;
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
@@ -125,6 +125,7 @@ __global__ void k_decide(Slot* slots, int nslots, SweepGeom g, SweepTotals* tot,
       active_list[atomicAdd(&cnt, 1)] = t;
     } else {
       s.active = 0;
+      if (nbox_all) nbox_all[s.src] = s.nbox;                           // per-source cost record for the balanced schedule
       atomicAdd(&tot->photon_loss, s.loss);                             // :233
       atomicAdd(&tot->sum_nbox, (unsigned long long)s.nbox);            // :236
     }
@@ -157,11 +158,17 @@ __global__ void k_secion_factors(const double* __restrict__ xh_av, size_t N3, do
 }
 
 // One shell radius r of every active source.  Work item = (active slot, cell of the shell).
+// Resident CTAs per SM: with the secondary-ionisation factors out of the band loop the single-SED kernels fit 96
+// registers with a 12..28-byte spill and gain 3 % from the fifth CTA (A/B on one box: 17.86 -> 17.31 ms per pass); the
+// multi-SED kernels would spill 164 bytes and stay at 4.
 #ifndef C2RAY_SWEEP_MINBLOCKS
-#define C2RAY_SWEEP_MINBLOCKS 4
+#define C2RAY_SWEEP_MINBLOCKS 5
+#endif
+#ifndef C2RAY_SWEEP_MINBLOCKS_MULTI
+#define C2RAY_SWEEP_MINBLOCKS_MULTI 4
 #endif
 template <bool ISO, bool MULTI>
-__global__ void __launch_bounds__(128, C2RAY_SWEEP_MINBLOCKS)
+__global__ void __launch_bounds__(128, MULTI ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS)
 k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot, SweepGeom g,
               GridPtrs G, double* __restrict__ scratch, int r) {
   const int nact = tot->nactive;
@@ -188,11 +195,6 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     const size_t p = (size_t)wrap0(i0 + di, m0) + (size_t)m0 * ((size_t)wrap0(j0 + dj, m1) + (size_t)m1 * wrap0(k0 + dk, m2));
     const double ndens_p = G.ndens[p];
     const double h_av0 = fmax(G.xh_av[p], epsilon);
-    SecIon yR = {0, 0, 0, 0, 0, 0};
-    if (!iso) {
-      yR.y1R0 = G.secion[p]; yR.y1R1 = G.secion[p + G.N3]; yR.y1R2 = G.secion[p + 2 * G.N3];
-      yR.y2R0 = G.secion[p + 3 * G.N3]; yR.y2R1 = G.secion[p + 4 * G.N3]; yR.y2R2 = G.secion[p + 5 * G.N3];
-    }
     const double he_av0 = fmax(G.xhe_av[p], epsilon);
     const double he_av1 = fmax(G.xhe_av[p + G.N3], epsilon);
 
@@ -295,10 +297,21 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
 
     PhotOut phi = {0, 0, 0, 0, 0, 0};
     if (cin_H < max_coldensh) {  // :250-270
-      phi = photoion_rates<ISO, MULTI>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, vol_ph, S.nflux, yR);
-      phi.photo_HI = fdiv(phi.photo_HI, h_av0 * ndens_p * (1.0 - abu_he));
-      phi.photo_HeI = fdiv(phi.photo_HeI, he_av0 * ndens_p * abu_he);
-      phi.photo_HeII = fdiv(phi.photo_HeII, he_av1 * ndens_p * abu_he);
+      double scale;
+      const PhotAcc A = photoion_bands<ISO, MULTI>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, S.nflux, scale);
+      // the cell's secondary-ionisation factors are only needed now: loading them after the band loop keeps twelve
+      // registers free while it runs
+      SecIon yR = {0, 0, 0, 0, 0, 0};
+      if (!iso) {
+        yR.y1R0 = __ldg(G.secion + p); yR.y1R1 = __ldg(G.secion + p + G.N3); yR.y1R2 = __ldg(G.secion + p + 2 * G.N3);
+        yR.y2R0 = __ldg(G.secion + p + 3 * G.N3); yR.y2R1 = __ldg(G.secion + p + 4 * G.N3); yR.y2R2 = __ldg(G.secion + p + 5 * G.N3);
+      }
+      phi = photoion_finish<ISO>(A, scale, vol_ph, yR);
+      // the cell's densities again (cache hits) rather than four values held in registers across the band loop
+      const double nd = __ldg(G.ndens + p);
+      phi.photo_HI = fdiv(phi.photo_HI, fmax(__ldg(G.xh_av + p), epsilon) * nd * (1.0 - abu_he));
+      phi.photo_HeI = fdiv(phi.photo_HeI, fmax(__ldg(G.xhe_av + p), epsilon) * nd * abu_he);
+      phi.photo_HeII = fdiv(phi.photo_HeII, fmax(__ldg(G.xhe_av + p + G.N3), epsilon) * nd * abu_he);
     }
     atomicAdd(G.rates + p, phi.photo_HI);                // :299-306
     atomicAdd(G.rates + G.N3 + p, phi.photo_HeI);

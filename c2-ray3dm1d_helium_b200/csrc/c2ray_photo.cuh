@@ -82,7 +82,10 @@ __device__ __forceinline__ SecIon secion_factors_fast(double i_state) {
 }
 
 struct PhotAcc {  // per-cell accumulators, still to be multiplied by 1/vol (except a_in, a_out)
-  double a_in, a_out, a_HI, a_HeI, a_HeII, f_heat, f_ion_HI, f_ion_HeI;
+  // s1..s4: band sums of f1ion.ph, f2ion.ph, f1heat.ph, f2heat.ph (ph = heating per species of a band).  The
+  // secondary-ionisation bookkeeping (:654-669, :739-759) is linear in them with band-independent factors y1R, y2R,
+  // so the factors are applied once per cell after the band loop instead of once per band.
+  double a_in, a_out, a_HI, a_HeI, a_HeII, f_heat, s1, s2, s3, s4;
 };
 
 struct CellCols {
@@ -93,7 +96,7 @@ struct CellCols {
 // MULTI = false: only the black-body SED exists in this run; NFlux is then factored out of the band loop.
 template <bool ISO, int NSP, bool MULTI>
 __device__ __forceinline__ void band_step(int b, const CellCols& c, const double nflux[3], const bool act[3],
-                                          const SecIon& y, PhotAcc& A) {
+                                          PhotAcc& A) {
   const int q = b - 1;
   const double sHI = d_band.sigma_HI[q];
   const double sHeI = NSP >= 2 ? d_band.sigma_HeI[q] : 0.0;
@@ -187,19 +190,18 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
         fs3 = fma(d_band.f1heat_HeII[q], ph_HeII, fs3);
         fs4 = fma(d_band.f2heat_HeII[q], ph_HeII, fs4);
       }
-      A.f_ion_HeI += y.y1R1 * fs1 - y.y2R1 * fs2;
-      A.f_ion_HI += y.y1R0 * fs1 - y.y2R0 * fs2;
-      df_heat = df_heat - y.y1R2 * fs3 + y.y2R2 * fs4;
+      A.s1 += fs1; A.s2 += fs2; A.s3 += fs3; A.s4 += fs4;
     }
     A.f_heat += df_heat;
   }
 }
 
 // vol: the shell-cell volume the rates are diluted over; nflux: NormFlux, NormFluxPL, NormFluxQPL of the source.
+// The band loop: everything of photoion_rates that does not need the cell's secondary-ionisation factors.  Returns the
+// accumulators and the flux scale still to be applied (photoion_finish).
 template <bool ISO, bool MULTI>
-__device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, double in_HeI, double out_HeI,
-                                                  double in_HeII, double out_HeII, double vol, const double nflux[3],
-                                                  const SecIon& y) {
+__device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, double in_HeI, double out_HeI,
+                                                  double in_HeII, double out_HeII, const double nflux[3], double& scale_out) {
   CellCols c;
   c.in_HI = in_HI; c.in_HeI = in_HeI; c.in_HeII = in_HeII;
   c.out_HI = out_HI; c.out_HeI = out_HeI; c.out_HeII = out_HeII;
@@ -223,12 +225,18 @@ __device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, d
     scale = nflux[0];
     if (!(scale > 0.0)) bhi = 0;  // :207 if (NormFlux(nsrc) > 0.0)
   }
-  PhotAcc A = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (blo <= NumBndin1 && bhi >= 1) band_step<ISO, 1, MULTI>(1, c, nflux, act, y, A);
+  PhotAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (blo <= NumBndin1 && bhi >= 1) band_step<ISO, 1, MULTI>(1, c, nflux, act, A);
   for (int b = max(blo, NumBndin1 + 1); b <= min(bhi, NumBndin1 + NumBndin2); b++)
-    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 2, MULTI>(b, c, nflux, act, y, A);
+    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 2, MULTI>(b, c, nflux, act, A);
   for (int b = max(blo, NumBndin1 + NumBndin2 + 1); b <= bhi; b++)
-    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 3, MULTI>(b, c, nflux, act, y, A);
+    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 3, MULTI>(b, c, nflux, act, A);
+  scale_out = scale;
+  return A;
+}
+
+template <bool ISO>
+__device__ __forceinline__ PhotOut photoion_finish(const PhotAcc& A, double scale, double vol, const SecIon& y) {
   const double rvol = fast_rcp(vol) * scale;
   PhotOut r;
   r.photo_in = A.a_in * scale;
@@ -238,11 +246,20 @@ __device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, d
   r.photo_HeII = A.a_HeII * rvol;
   r.heat = 0.0;
   if (!ISO) {
-    r.heat = A.f_heat * rvol;
-    r.photo_HI += A.f_ion_HI * rvol * (1.0 / (ion_freq_HI * hplanck));     // :773-777
-    r.photo_HeI += A.f_ion_HeI * rvol * (1.0 / (ion_freq_HeI * hplanck));
+    r.heat = (A.f_heat - y.y1R2 * A.s3 + y.y2R2 * A.s4) * rvol;                                    // :669, :759
+    r.photo_HI += (y.y1R0 * A.s1 - y.y2R0 * A.s2) * rvol * (1.0 / (ion_freq_HI * hplanck));        // :773-777
+    r.photo_HeI += (y.y1R1 * A.s1 - y.y2R1 * A.s2) * rvol * (1.0 / (ion_freq_HeI * hplanck));
   }
   return r;
+}
+
+template <bool ISO, bool MULTI>
+__device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, double in_HeI, double out_HeI,
+                                                  double in_HeII, double out_HeII, double vol, const double nflux[3],
+                                                  const SecIon& y) {
+  double scale;
+  const PhotAcc A = photoion_bands<ISO, MULTI>(in_HI, out_HI, in_HeI, out_HeI, in_HeII, out_HeII, nflux, scale);
+  return photoion_finish<ISO>(A, scale, vol, y);
 }
 
 // Re-pack the four (0:NumTau, 1:nb) tables of one SED into band-major 64-byte rows.  One thread per (band, row).

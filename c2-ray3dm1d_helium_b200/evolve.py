@@ -316,6 +316,17 @@ class C2Ray:
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         capi.check(self.lib.c2ray_b200_comm_init(self.ctx, buf, C.c_int32(rank), C.c_int32(npr)))
 
+    def set_source_schedule(self, mode):
+        """0: do_grid_static round robin (master_slave.F90:85); 1: balanced by the last pass's sub-box counts."""
+        capi.check(self.lib.c2ray_b200_set_source_schedule(self.ctx, C.c_int32(mode)))
+
+    def my_sources(self):
+        n = C.c_int32()
+        capi.check(self.lib.c2ray_b200_my_sources(self.ctx, None, C.c_int32(0), C.byref(n)))
+        ids = np.zeros(max(n.value, 1), dtype=np.int32)
+        capi.check(self.lib.c2ray_b200_my_sources(self.ctx, _p(ids), C.c_int32(n.value), C.byref(n)))
+        return ids[:n.value]
+
     def set_rank(self, rank, npr):
         capi.check(self.lib.c2ray_b200_set_rank(self.ctx, C.c_int32(rank), C.c_int32(npr)))
 
@@ -361,6 +372,14 @@ def fortran_records_read(path, specs):
     sizes = (C.c_int64 * n)(*[a.nbytes for a in arrays])
     capi.check(capi.load().c2ray_b200_fortran_records_read(os.fsencode(path), C.c_int32(n), ptrs, sizes))
     return arrays
+
+
+def balanced_partition(cost, npr):
+    """owner[i] = rank that traces source i under the balanced schedule (longest processing time first)."""
+    cost = np.ascontiguousarray(cost, dtype=np.int64)
+    owner = np.zeros(len(cost), dtype=np.int32)
+    capi.check(capi.load().c2ray_b200_balanced_partition(C.c_int32(len(cost)), _p(cost), C.c_int32(npr), _p(owner)))
+    return owner
 
 
 def source_partition(NumSrc, rank, npr):

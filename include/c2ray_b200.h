@@ -215,6 +215,16 @@ int c2ray_b200_comm_unique_id(uint8_t id[128]);
 int c2ray_b200_comm_init(c2ray_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t npr);
 /* rank / npr without a communicator: source partition only (used by tests and by hosts that reduce themselves) */
 int c2ray_b200_set_rank(c2ray_ctx* ctx, int32_t rank, int32_t npr);
+/* Which rank traces which source.  0: the reference's static model, ns1 = 1+rank, NumSrc, npr (master_slave.F90:74-96
+ * do_grid_static), the default.  1: balanced -- the stand-in for the master/slave model (master_slave.F90:124-326): after
+ * every pass the ranks exchange each source's sub-box count and the sources are re-dealt, most expensive first, to the
+ * least loaded rank (needs a communicator; the first pass is the round-robin deal).  Results differ from schedule 0 only
+ * in the order the rate grids are summed. */
+int c2ray_b200_set_source_schedule(c2ray_ctx* ctx, int32_t mode);
+/* the deal itself, on host data: owner[i] = rank of source i given cost[i] (deterministic; every rank computes it) */
+int c2ray_b200_balanced_partition(int32_t NumSrc, const int64_t* cost, int32_t npr, int32_t* owner);
+/* 1-based numbers of the sources this rank traces in the next pass (ids may be NULL to query the count) */
+int c2ray_b200_my_sources(c2ray_ctx* ctx, int32_t* ids, int32_t cap, int32_t* n);
 /* device pointer + element count of the contiguous [phih | phihe(0) | phihe(1) | phiheat | photon_loss(47) |
  * sum_nbox] FP64 buffer, for hosts that run their own reduction on it */
 int c2ray_b200_rates_device_buffer(c2ray_ctx* ctx, void** dptr, int64_t* count);

@@ -91,3 +91,20 @@ def test_source_partition_is_do_grid_static():
     assert c2ray_b200.source_partition(2, 3, 4) == []
     allsrc = sorted(sum((c2ray_b200.source_partition(1000, r, 8) for r in range(8)), []))
     assert allsrc == list(range(1, 1001))
+
+
+def test_balanced_partition_is_a_deterministic_lpt_deal():
+    """The stand-in for the master/slave hand-out (master_slave.F90:124-326): every source exactly once, heavy sources
+    spread first, never worse than the static round robin on a skewed cost list, identical on every call."""
+    rng = np.random.default_rng(3)
+    cost = (rng.pareto(1.5, 500) * 1000 + 100).astype(np.int64)
+    for npr in (1, 2, 3, 8):
+        owner = c2ray_b200.balanced_partition(cost, npr)
+        assert owner.min() >= 0 and owner.max() < npr and np.array_equal(owner, c2ray_b200.balanced_partition(cost, npr))
+        load = np.bincount(owner, weights=cost, minlength=npr)
+        static = np.array([cost[r::npr].sum() for r in range(npr)])
+        assert load.max() <= static.max()
+        assert load.max() <= load.mean() + cost.max()          # the LPT bound
+    # equal costs reproduce do_grid_static's round robin
+    assert list(c2ray_b200.balanced_partition(np.full(10, 7), 4)) == [0, 1, 2, 3, 0, 1, 2, 3, 0, 1]
+    assert c2ray_b200.balanced_partition(np.zeros(0, dtype=np.int64), 4).size == 0

@@ -22,19 +22,21 @@ import torch.distributed as dist
 import c2ray_b200
 
 
-def run(p, local, uid, rank, world, split, steps):
+def run(p, local, uid, rank, world, split, steps, schedule=0):
     os.environ["C2RAY_SPLIT_CHEM"] = "1" if split else "0"
     c = c2ray_b200.from_problem(p, device=local, deterministic=True)
     if uid is not None:
         c.comm_init(uid, rank, world)
+        c.set_source_schedule(schedule)
     hist = []
     for s in range(steps):
         st = c.evolve3D(0.0, p["dt"], 0)
         hist.append((st["niter"], tuple(int(x) for x in st["conv_hist"]), st["sum_nbox_all"], st["photon_loss_all"],
                      st["photcons"], st["ms_chem"], st["ms_allreduce"], st["ms_sweep"]))
     out = c.get_state() + tuple(c.get_rates()) + tuple(c.get_work_state())
+    mine = list(c.my_sources())
     c.close()
-    return hist, out
+    return hist, out + (mine,)
 
 
 def relerr(a, b):
@@ -60,7 +62,19 @@ def main():
     h_split, s_split = run(p, local, uid(), rank, world, True, steps)
     h_repl, s_repl = run(p, local, uid(), rank, world, False, steps)
     h_one, s_one = run(p, local, None, 0, 1, False, steps)
+    h_bal, s_bal = run(p, local, uid(), rank, world, True, steps, schedule=1)
+    mine_static, mine_bal = s_split[-1], s_bal[-1]
+    s_split, s_repl, s_one, s_bal = s_split[:-1], s_repl[:-1], s_one[:-1], s_bal[:-1]
     ok = True
+    # the balanced schedule: same integer histories, same fields to summation order, every source dealt exactly once
+    counts = torch.zeros(len(p["NormFlux"]) + 1, dtype=torch.int32, device="cuda")
+    counts[torch.tensor(mine_bal, dtype=torch.long, device="cuda")] += 1
+    dist.all_reduce(counts)
+    ok &= bool((counts[1:] == 1).all().item()) and int(counts[0].item()) == 0
+    for a, b in zip(h_bal, h_one):
+        ok &= a[:3] == b[:3]
+    e_bal = max(float(np.max(np.abs(x - y) / (1e-8 * np.abs(y) + 2e-10))) for x, y in zip(s_bal[:2], s_one[:2]))
+    ok &= e_bal < 1
     # integer histories: niter, conv_flag per iteration, sum_nbox
     for a, b, c1 in zip(h_split, h_repl, h_one):
         ok &= a[:3] == b[:3] == c1[:3]
@@ -90,6 +104,7 @@ def main():
     print(f"rank {rank}/{world}: mesh {mesh} sources {nsrc} niter {[h[0] for h in h_split]} split-vs-replicated {e_sr:.2e} "
           f"(tol {tol_sr:g}) vs-one-rank err/tol {max(errs.values()):.3f} all-ranks-equal {same} | ms sweep/chem/comm split "
           f"{ms(h_split)[0]:.1f}/{ms(h_split)[1]:.1f}/{ms(h_split)[2]:.1f} replicated {ms(h_repl)[0]:.1f}/{ms(h_repl)[1]:.1f}/{ms(h_repl)[2]:.1f}"
+          f" | balanced schedule: sources {mine_static} -> {mine_bal}, err/tol {e_bal:.3f}"
           f" -> {'OK' if ok else 'MISMATCH'}", flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
