@@ -4,8 +4,9 @@
 Metric: source x cell RT updates/s (BASELINE.json), whole job, over full evolve3D time steps (ray-tracing sweeps of all
 sources + rate-grid reduction + global chemistry passes, iterated to convergence).
 Workload (N=1): BASELINE configs[1] -- Test-4 style 128^3 lognormal box, 16 black-body sources (T_eff=1e5 K,
-subboxsize=mesh), non-isothermal.  For N>1 every rank gets 16 sources of the same box (weak scaling), the rate grids are
-summed with one NCCL allreduce per iteration and the chemistry pass is replicated, as in the reference.
+subboxsize=mesh), non-isothermal.  For N>1 every rank gets 16 sources of the same box (weak scaling); per iteration the
+rate grids are reduce-scattered, every rank runs the global pass on its N^3/npr cells and the fractions the next sweep
+reads are all-gathered (the reference: allreduce + replicated pass; same results, see tools/multi_gpu_check.py).
 A step = one evolve3D(time,dt) from the same start state (device snapshot restored inside the timed region).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
@@ -51,7 +52,10 @@ def config_dict(p, n_gpus):
                         f"{len(p['NormFlux'])} BB sources T_eff=1e5 K, subboxsize=mesh, non-isothermal, dt=0.05 Myr, "
                         "one full evolve3D time step per step",
             "mesh": int(p["mesh"][0]), "sources": int(len(p["NormFlux"])), "sources_per_gpu": SRC_PER_GPU,
-            "parallelism": f"sources round-robin over {n_gpus} GPU(s), replicated chemistry",
+            "parallelism": ("one GPU" if n_gpus == 1 else
+                            f"sources round-robin over {n_gpus} GPUs (do_grid_static); per iteration one reduce-scatter of the "
+                            "rate grids, the global pass on N^3/npr cells per rank, one all-gather of the fractions the next "
+                            "sweep reads"),
             "l2_policy": "per-step working set (state + rate grids + snapshot, >400 MB) exceeds the 126 MB L2"}
 
 

@@ -397,7 +397,7 @@ int sweep_all(c2ray_ctx* c) {
     GridPtrs G{c->ndens, c->xh_av, c->xhe_av, c->rates, c->d_secion, c->N3, c->lls_type, c->coldensh_LLS, c->d_lls};
     const int batch = c->par.deterministic ? 1 : c->slots_cap;
     ngroups = c->par.deterministic ? 1 : std::max(1, std::min(c->sweep_groups, std::min(batch, c->n_mine)));
-    const int max_blocks = 148 * 16;
+    static const int max_blocks = [] { const char* e = getenv("C2RAY_SWEEP_MAXBLOCKS"); return e ? std::max(1, atoi(e)) : 148 * 16; }();
     // A source whose PL and QPL fluxes are zero (or whose tables are absent) contributes through the black-body
     // tables only and takes the single-SED kernel, whatever other sources need: in a -DQUASARS run with QPL flux
     // on a few bright sources the rest do not pay for the three-SED loop.  The list is ordered single-SED sources

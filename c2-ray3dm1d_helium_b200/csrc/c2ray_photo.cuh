@@ -10,19 +10,31 @@
 //   * reciprocals use MUFU.RCP64H + cubic/Newton refinement (error ~ 2^-54) without the IEEE slow path
 //   * the secondary-ionisation factors y1R, y2R (9 pow per cell in the reference, :557-565) depend on the cell only
 //     and are precomputed once per iteration by k_secion_factors
-//   * the four tables of an SED are re-packed band-major into 64-byte rows
-//       row(band, itau) = [photo_thick, heat_thick(HI,HeI,HeII), photo_thin, heat_thin(HI,HeI,HeII)]
-//     so one table position is two adjacent rows (128 contiguous bytes, 16-byte vector loads) instead of up to 16
-//     scalar gathers from different columns; row NumTau+1 duplicates row NumTau (ipos_p1 = min(NumTau, ipos+1))
+//   * the four tables of an SED are re-packed band-major into 32-byte rows, thick and thin values apart:
+//       thick(band, itau) = [photo_thick, heat_thick(HI,HeI,HeII)]   thin(band, itau) = [photo_thin, heat_thin(HI,HeI,HeII)]
+//     so one table position is two adjacent rows (64 contiguous bytes, 16-byte vector loads) instead of up to 8
+//     scalar gathers from different columns, and the common optically thick cell never pulls thin values through
+//     the L1; row NumTau+1 duplicates row NumTau (ipos_p1 = min(NumTau, ipos+1))
 //   * the band loop is split by band group (1 / 26 / 20 sub-bands) with the species count as a template parameter
 // All of this changes results at the 1e-15 level; the parity tests hold 1e-8.
 #pragma once
 #include "c2ray_physics.cuh"
 
+// tuning builds only: -DC2RAY_BAND_UNROLL=n unrolls the band loops
+#ifdef C2RAY_BAND_UNROLL
+#define C2_STR2(x) #x
+#define C2_STR(x) C2_STR2(x)
+#define C2_BAND_UNROLL _Pragma(C2_STR(unroll C2RAY_BAND_UNROLL))
+#else
+#define C2_BAND_UNROLL
+#endif
+
 namespace c2 {
 
-constexpr int PK_ROW = 8;                 // doubles per packed row
+constexpr int PK_ROW = 8;                 // doubles per table position: 4 thick + 4 thin values
+constexpr int PK_HALF = 4;                // doubles per packed row (thick rows and thin rows are separate arrays)
 constexpr int PK_ROWS = NumTau + 2;       // rows per band (one duplicate at the end)
+constexpr size_t PK_THIN_OFF = (size_t)NumFreqBnd * PK_ROWS * PK_HALF;  // the thin rows follow all thick rows
 
 // column_density.f90:351-376 with the fast reciprocal
 __device__ __forceinline__ double weightf_fast(double cd, double sig) { return fast_rcp(fmax(0.6, cd * sig)); }
@@ -123,8 +135,8 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
   }
   double phot = 0.0;                                  // absorbed photons of this band, all SEDs
   double ph_HI = 0.0, ph_HeI = 0.0, ph_HeII = 0.0;    // heating per species of this band, all SEDs
-  const size_t row_in = ((size_t)q * PK_ROWS + pin.ipos) * PK_ROW;
-  const size_t row_out = ((size_t)q * PK_ROWS + pout.ipos) * PK_ROW;
+  const size_t row_in = ((size_t)q * PK_ROWS + pin.ipos) * PK_HALF;
+  const size_t row_out = ((size_t)q * PK_ROWS + pout.ipos) * PK_HALF;
 #pragma unroll
   for (int s = 0; s < (MULTI ? 3 : 1); s++) {
     if (MULTI) {
@@ -134,17 +146,18 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
     const double NFlux = MULTI ? nflux[s] : 1.0;
     const double* ri = pk + row_in;
     const double* ro = pk + row_out;
+    const double* ti = ri + PK_THIN_OFF;  // thin rows at tau_in
     // thick values at tau_in: [photo_thick, heat_thick HI | heat_thick HeI, heat_thick HeII]
-    const double2 i0a = ld2(ri), i1a = ld2(ri + PK_ROW);
+    const double2 i0a = ld2(ri), i1a = ld2(ri + PK_HALF);
     const double phi_in = NFlux * lerp(i0a.x, i1a.x, pin.residual);  // photo_lookuptable :390-396
     double phi_all, phi_out;
     double2 o0a = i0a, o1a = i1a;
     if (thick_p) {
-      o0a = ld2(ro); o1a = ld2(ro + PK_ROW);
+      o0a = ld2(ro); o1a = ld2(ro + PK_HALF);
       phi_out = NFlux * lerp(o0a.x, o1a.x, pout.residual);
       phi_all = phi_in - phi_out;
     } else {
-      const double thin = lerp(__ldg(ri + 4), __ldg(ri + PK_ROW + 4), pin.residual);
+      const double thin = lerp(__ldg(ti), __ldg(ti + PK_HALF), pin.residual);
       phi_all = NFlux * dtau * thin;
       phi_out = phi_in - phi_all;
     }
@@ -155,17 +168,17 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
       if (thick_h) {
         ph_HI = fma(scHI, NFlux * (lerp(i0a.y, i1a.y, pin.residual) - lerp(o0a.y, o1a.y, pout.residual)), ph_HI);
         if (NSP >= 2) {
-          const double2 i0b = ld2(ri + 2), i1b = ld2(ri + PK_ROW + 2), o0b = ld2(ro + 2), o1b = ld2(ro + PK_ROW + 2);
+          const double2 i0b = ld2(ri + 2), i1b = ld2(ri + PK_HALF + 2), o0b = ld2(ro + 2), o1b = ld2(ro + PK_HALF + 2);
           ph_HeI = fma(scHeI, NFlux * (lerp(i0b.x, i1b.x, pin.residual) - lerp(o0b.x, o1b.x, pout.residual)), ph_HeI);
           if (NSP == 3)
             ph_HeII = fma(scHeII, NFlux * (lerp(i0b.y, i1b.y, pin.residual) - lerp(o0b.y, o1b.y, pout.residual)), ph_HeII);
         }
       } else {
         // thin rows at tau_in: [photo_thin, heat_thin HI | heat_thin HeI, heat_thin HeII]
-        const double2 t0a = ld2(ri + 4), t1a = ld2(ri + PK_ROW + 4);
+        const double2 t0a = ld2(ti), t1a = ld2(ti + PK_HALF);
         ph_HI = fma(NFlux * tcHI, lerp(t0a.y, t1a.y, pin.residual), ph_HI);
         if (NSP >= 2) {
-          const double2 t0b = ld2(ri + 6), t1b = ld2(ri + PK_ROW + 6);
+          const double2 t0b = ld2(ti + 2), t1b = ld2(ti + PK_HALF + 2);
           ph_HeI = fma(NFlux * tcHeI, lerp(t0b.x, t1b.x, pin.residual), ph_HeI);
           if (NSP == 3) ph_HeII = fma(NFlux * tcHeII, lerp(t0b.y, t1b.y, pin.residual), ph_HeII);
         }
@@ -227,8 +240,10 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
   }
   PhotAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (blo <= NumBndin1 && bhi >= 1) band_step<ISO, 1, MULTI>(1, c, nflux, act, A);
+  C2_BAND_UNROLL
   for (int b = max(blo, NumBndin1 + 1); b <= min(bhi, NumBndin1 + NumBndin2); b++)
     if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 2, MULTI>(b, c, nflux, act, A);
+  C2_BAND_UNROLL
   for (int b = max(blo, NumBndin1 + NumBndin2 + 1); b <= bhi; b++)
     if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 3, MULTI>(b, c, nflux, act, A);
   scale_out = scale;
@@ -262,7 +277,7 @@ __device__ __forceinline__ PhotOut photoion_rates(double in_HI, double out_HI, d
   return photoion_finish<ISO>(A, scale, vol, y);
 }
 
-// Re-pack the four (0:NumTau, 1:nb) tables of one SED into band-major 64-byte rows.  One thread per (band, row).
+// Re-pack the four (0:NumTau, 1:nb) tables of one SED into band-major 32-byte thick and thin rows.  One thread per (band, row).
 __global__ void k_pack_tables(const double* __restrict__ photo_thick, const double* __restrict__ photo_thin,
                               const double* __restrict__ heat_thick, const double* __restrict__ heat_thin,
                               double* __restrict__ packed) {
@@ -279,7 +294,10 @@ __global__ void k_pack_tables(const double* __restrict__ photo_thick, const doub
       v[1 + sp] = heat_thick[(size_t)(hcol + sp) * (NumTau + 1) + it];
       v[5 + sp] = heat_thin[(size_t)(hcol + sp) * (NumTau + 1) + it];
     }
-  for (int k = 0; k < PK_ROW; k++) packed[(size_t)t * PK_ROW + k] = v[k];
+  for (int k = 0; k < PK_HALF; k++) {
+    packed[(size_t)t * PK_HALF + k] = v[k];
+    packed[PK_THIN_OFF + (size_t)t * PK_HALF + k] = v[PK_HALF + k];
+  }
 }
 
 }  // namespace c2

@@ -53,6 +53,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     p = c2ray_b200.synth.make_problem(2, n=mesh, num_src=nsrc, isothermal=False)
+    p["subboxsize"] = 5  # sub-box counts (the balanced schedule's cost) then differ from source to source
 
     def uid():
         u = [c2ray_b200.C2Ray.comm_unique_id() if rank == 0 else None]
