@@ -84,6 +84,7 @@ constexpr int NCCL_INT32 = 2, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0, 
 }  // namespace
 
 constexpr int MAX_SWEEP_GROUPS = 8;
+constexpr int SPLIT_LANES = 8;  // lanes sharing a cell in latency-bound sweep launches
 
 struct c2ray_ctx {
   int device = 0;
@@ -126,6 +127,7 @@ struct c2ray_ctx {
   cudaStream_t gstream[MAX_SWEEP_GROUPS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_SWEEP_GROUPS] = {};
   int sweep_groups = 2;                     // env C2RAY_SWEEP_GROUPS
+  int sweep_split = 1;                      // env C2RAY_SWEEP_SPLIT: band-split kernel for launches that cannot fill the GPU
   double* d_scratch = nullptr;
   int slots_cap = 0;
   bool slots_budget_limited = false;
@@ -463,13 +465,21 @@ int sweep_all(c2ray_ctx* c) {
         for (int r = r_lo; r <= r_hi; r++) {
           for (int q = 0; q < ngroups; q++) {
             if (nact[q] <= 0) continue;
-            const long long items = (long long)nact[q] * (r == 0 ? 1 : 24LL * r * r + 2);
+            const long long cells = (long long)nact[q] * (r == 0 ? 1 : 24LL * r * r + 2);
+            // fewer cells than resident threads: latency bound, SPLIT_LANES lanes share a cell (see k_sweep_shell)
+            const long long resident = 148LL * 128 * (multi_sed ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS);
+            // measured: pays off below a quarter of the resident threads (12 % on 1250 sources x r <= 10, 9 % on one
+            // source at 128^3), costs 1 % at a full wave (redundant geometry)
+            const bool split = c->sweep_split && cells * ngroups * 4 <= resident;
+            const long long items = cells * (split ? SPLIT_LANES : 1);
             const int blocks = (int)std::min<long long>((items + 127) / 128, max_blocks);
-#define SWEEP(ISO, MULTI)                                                                                              \
-  LAUNCH_S(c, c->gstream[q], (k_sweep_shell<ISO, MULTI>), blocks, 128, c->d_slots + goff[q], c->d_active + goff[q], \
+#define SWEEP(ISO, MULTI, LANES)                                                                                              \
+  LAUNCH_S(c, c->gstream[q], (k_sweep_shell<ISO, MULTI, LANES>), blocks, 128, c->d_slots + goff[q], c->d_active + goff[q], \
            c->d_gtot + q, g, G, c->d_scratch + (size_t)goff[q] * slot_stride, r)
-            if (multi_sed) { if (c->par.isothermal) SWEEP(true, true); else SWEEP(false, true); }
-            else { if (c->par.isothermal) SWEEP(true, false); else SWEEP(false, false); }
+#define SWEEP2(ISO, MULTI) do { if (split) SWEEP(ISO, MULTI, SPLIT_LANES); else SWEEP(ISO, MULTI, 1); } while (0)
+            if (multi_sed) { if (c->par.isothermal) SWEEP2(true, true); else SWEEP2(false, true); }
+            else { if (c->par.isothermal) SWEEP2(true, false); else SWEEP2(false, false); }
+#undef SWEEP2
 #undef SWEEP
           }
         }
@@ -782,6 +792,7 @@ int c2ray_b200_init(const c2ray_params* params, const int32_t mesh[3], int32_t d
   for (auto& st : c->gstream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   for (auto& ev : c->ev_join) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  if (const char* e = getenv("C2RAY_SWEEP_SPLIT")) c->sweep_split = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_GROUPS")) c->sweep_groups = std::max(1, std::min(MAX_SWEEP_GROUPS, atoi(e)));
   CK(cudaMalloc(&c->d_chem, sizeof(ChemTotals)));
   CK(cudaMalloc(&c->d_sums, 5 * sizeof(double)));

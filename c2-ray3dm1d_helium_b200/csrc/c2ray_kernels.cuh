@@ -167,13 +167,20 @@ __global__ void k_secion_factors(const double* __restrict__ xh_av, size_t N3, do
 #ifndef C2RAY_SWEEP_MINBLOCKS_MULTI
 #define C2RAY_SWEEP_MINBLOCKS_MULTI 4
 #endif
-template <bool ISO, bool MULTI>
+// LANES (1 or a power of two <= 32): lanes of a warp that share one cell, each taking every LANES-th frequency band.
+// One update is a dependent chain of ~9 k instructions, ~25 us for a warp on its own; a launch that cannot fill the
+// machine (the inner shells, few sources) is bound by that latency, not by throughput, and finishes LANES times sooner
+// when the chain is cut into LANES pieces.  The geometry part is computed redundantly by the sharing lanes; lane 0 of a
+// cell writes.  Launches with more cells than resident threads use LANES = 1.
+template <bool ISO, bool MULTI, int LANES>
 __global__ void __launch_bounds__(128, MULTI ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS)
 k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot, SweepGeom g,
               GridPtrs G, double* __restrict__ scratch, int r) {
   const int nact = tot->nactive;
   const int ncell = shell_cells(r);
-  const long long total = (long long)nact * ncell;
+  const long long total = (long long)nact * ncell * LANES;
+  const int lane_j = LANES > 1 ? (int)(threadIdx.x & (LANES - 1)) : 0;
+  const unsigned lane_mask = LANES > 1 ? ((LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u)) << (threadIdx.x & 31 & ~(LANES - 1))) : 0u;
   const size_t slot_stride = (size_t)6 * g.cap;                 // [parity][species][cap]
   const int par = r & 1;
   constexpr bool iso = ISO;
@@ -181,8 +188,9 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
   unsigned int done = 0;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
-    const int a = (int)(t / ncell);
-    const int c = (int)(t - (long long)a * ncell);
+    const long long item = LANES > 1 ? t / LANES : t;   // the LANES lanes of an aligned group share the item
+    const int a = (int)(item / ncell);
+    const int c = (int)(item - (long long)a * ncell);
     const int sid = active_list[a];
     Slot& S = slots[sid];
     int di, dj, dk;
@@ -293,12 +301,13 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     const double cout_H = cin_H + h_av0 * ndens_p * path * (1.0 - abu_he);
     const double cout_He0 = cin_He0 + he_av0 * ndens_p * path * abu_he;
     const double cout_He1 = cin_He1 + he_av1 * ndens_p * path * abu_he;
-    cur[c] = cout_H; cur[g.cap + c] = cout_He0; cur[2 * g.cap + c] = cout_He1;
+    if (lane_j == 0) { cur[c] = cout_H; cur[g.cap + c] = cout_He0; cur[2 * g.cap + c] = cout_He1; }
 
     PhotOut phi = {0, 0, 0, 0, 0, 0};
     if (cin_H < max_coldensh) {  // :250-270
       double scale;
-      const PhotAcc A = photoion_bands<ISO, MULTI>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, S.nflux, scale);
+      PhotAcc A = photoion_bands<ISO, MULTI, LANES>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, S.nflux, scale, lane_j);
+      if (LANES > 1) reduce_bands<ISO, LANES>(A, lane_mask);  // the branch above is uniform over the lanes of a cell
       // the cell's secondary-ionisation factors are only needed now: loading them after the band loop keeps twelve
       // registers free while it runs
       SecIon yR = {0, 0, 0, 0, 0, 0};
@@ -313,6 +322,7 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
       phi.photo_HeI = fdiv(phi.photo_HeI, fmax(__ldg(G.xhe_av + p), epsilon) * nd * abu_he);
       phi.photo_HeII = fdiv(phi.photo_HeII, fmax(__ldg(G.xhe_av + p + G.N3), epsilon) * nd * abu_he);
     }
+    if (LANES > 1 && lane_j != 0) continue;              // one lane per cell publishes
     atomicAdd(G.rates + p, phi.photo_HI);                // :299-306
     atomicAdd(G.rates + G.N3 + p, phi.photo_HeI);
     atomicAdd(G.rates + 2 * G.N3 + p, phi.photo_HeII);

@@ -212,9 +212,12 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
 // vol: the shell-cell volume the rates are diluted over; nflux: NormFlux, NormFluxPL, NormFluxQPL of the source.
 // The band loop: everything of photoion_rates that does not need the cell's secondary-ionisation factors.  Returns the
 // accumulators and the flux scale still to be applied (photoion_finish).
-template <bool ISO, bool MULTI>
+// LANES > 1: the bands of a cell are dealt to LANES adjacent lanes of a warp (lane_j = 0..LANES-1 takes every
+// LANES-th band of each band group); the caller sums the accumulators over those lanes (reduce_bands).
+template <bool ISO, bool MULTI, int LANES = 1>
 __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, double in_HeI, double out_HeI,
-                                                  double in_HeII, double out_HeII, const double nflux[3], double& scale_out) {
+                                                  double in_HeII, double out_HeII, const double nflux[3], double& scale_out,
+                                                  int lane_j = 0) {
   CellCols c;
   c.in_HI = in_HI; c.in_HeI = in_HeI; c.in_HeII = in_HeII;
   c.out_HI = out_HI; c.out_HeI = out_HeI; c.out_HeII = out_HeII;
@@ -239,15 +242,35 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
     if (!(scale > 0.0)) bhi = 0;  // :207 if (NormFlux(nsrc) > 0.0)
   }
   PhotAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (blo <= NumBndin1 && bhi >= 1) band_step<ISO, 1, MULTI>(1, c, nflux, act, A);
+  if (blo <= NumBndin1 && bhi >= 1 && lane_j == 0) band_step<ISO, 1, MULTI>(1, c, nflux, act, A);
   C2_BAND_UNROLL
-  for (int b = max(blo, NumBndin1 + 1); b <= min(bhi, NumBndin1 + NumBndin2); b++)
+  for (int b = max(blo, NumBndin1 + 1) + lane_j; b <= min(bhi, NumBndin1 + NumBndin2); b += LANES)
     if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 2, MULTI>(b, c, nflux, act, A);
   C2_BAND_UNROLL
-  for (int b = max(blo, NumBndin1 + NumBndin2 + 1); b <= bhi; b++)
+  for (int b = max(blo, NumBndin1 + NumBndin2 + 1) + lane_j; b <= bhi; b += LANES)
     if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 3, MULTI>(b, c, nflux, act, A);
   scale_out = scale;
   return A;
+}
+
+// Sum of the band accumulators over the LANES lanes that shared a cell (mask: exactly those lanes).
+template <bool ISO, int LANES>
+__device__ __forceinline__ void reduce_bands(PhotAcc& A, unsigned mask) {
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+    A.a_in += __shfl_xor_sync(mask, A.a_in, o);
+    A.a_out += __shfl_xor_sync(mask, A.a_out, o);
+    A.a_HI += __shfl_xor_sync(mask, A.a_HI, o);
+    A.a_HeI += __shfl_xor_sync(mask, A.a_HeI, o);
+    A.a_HeII += __shfl_xor_sync(mask, A.a_HeII, o);
+    if (!ISO) {
+      A.f_heat += __shfl_xor_sync(mask, A.f_heat, o);
+      A.s1 += __shfl_xor_sync(mask, A.s1, o);
+      A.s2 += __shfl_xor_sync(mask, A.s2, o);
+      A.s3 += __shfl_xor_sync(mask, A.s3, o);
+      A.s4 += __shfl_xor_sync(mask, A.s4, o);
+    }
+  }
 }
 
 template <bool ISO>

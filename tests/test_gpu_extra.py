@@ -8,7 +8,7 @@ import pytest
 import c2ray_b200
 from c2ray_b200 import capi
 from oracle import oracle as O
-from common import oracle_setup, oracle_grid, relerr, frac_err
+from common import oracle_setup, oracle_grid, relerr, frac_err, partially_ionized_state
 
 pytestmark = pytest.mark.gpu
 synth = c2ray_b200.synth
@@ -190,3 +190,31 @@ def test_all_three_seds():
             scale = np.abs(ref).max(axis=1, keepdims=True)
             assert np.max(np.abs(got - ref) / (np.abs(ref) + 1e-250 + 1e-14 * scale)) < 1e-9, (sed, kind)
     c.close(); c2.close()
+
+
+def test_band_split_and_plain_sweep_kernels_agree(monkeypatch):
+    """Launches that cannot fill the GPU deal the frequency bands of a cell to 8 lanes (k_sweep_shell<.., LANES=8>);
+    big launches use one lane per cell.  On a small mesh every launch is of the first kind, so the plain kernel is
+    forced here and both are compared with each other (summation order only) and with the oracle."""
+    p = synth.make_problem(3, n=20, num_src=4)
+    tables = oracle_setup(p)
+    g = oracle_grid(p)
+    xh_av, xhe_av = partially_ionized_state(p)
+    res = []
+    for split in ("1", "0"):
+        monkeypatch.setenv("C2RAY_SWEEP_SPLIT", split)
+        c = c2ray_b200.from_problem(p, tables=tables)
+        c.set_work_state(xh_av, xhe_av, xh_av, xhe_av)
+        c.set_rates_to_zero()
+        upd = c.pass_all_sources(1, p["dt"])
+        res.append((upd, c.get_rates()))
+        c.close()
+    g.set_work_state(xh_av, xhe_av, xh_av, xhe_av)
+    g.set_rates_to_zero()
+    upd_o = g.pass_all_sources(order=1)[0]
+    ref = g.get_rates()
+    assert res[0][0] == res[1][0] == upd_o
+    for a, b, o in zip(res[0][1], res[1][1], ref):
+        assert np.array_equal(a != 0, o != 0) and np.array_equal(b != 0, o != 0)
+        assert relerr(a, b, 1e-300) < 1e-12
+        assert relerr(a, o, 1e-300) < 1e-8 and relerr(b, o, 1e-300) < 1e-8
