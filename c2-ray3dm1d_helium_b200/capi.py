@@ -25,7 +25,7 @@ EXPORTS = [
     "c2ray_b200_set_dump", "c2ray_b200_write_iteration_dump", "c2ray_b200_read_iteration_dump",
     "c2ray_b200_write_stream2", "c2ray_b200_write_stream3", "c2ray_b200_fortran_records_write",
     "c2ray_b200_fortran_records_read", "c2ray_b200_set_clumping_grid", "c2ray_b200_set_LLS",
-    "c2ray_b200_set_source_schedule", "c2ray_b200_balanced_partition", "c2ray_b200_my_sources",
+    "c2ray_b200_set_source_schedule", "c2ray_b200_balanced_partition", "c2ray_b200_my_sources", "c2ray_b200_mrgrnk",
 ]
 
 
@@ -77,7 +77,12 @@ def load():
     L.c2ray_b200_launch_count.restype = C.c_int64
     L.c2ray_b200_launch_count.argtypes = [C.c_void_p]
     for name in EXPORTS:
-        fn = getattr(L, name)
+        try:
+            fn = getattr(L, name)
+        except AttributeError:
+            if "C2RAY_B200_LIB" in os.environ:  # an older tuning build loaded for an A/B timing
+                continue
+            raise
         if name not in ("c2ray_b200_last_error", "c2ray_b200_launch_count"):
             fn.restype = C.c_int
     _lib = L

@@ -5,6 +5,7 @@
 //
 // No CPU fallback: every compute entry point needs a CUDA device and fails with C2RAY_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <algorithm>
 #include <chrono>
@@ -134,7 +135,7 @@ struct c2ray_ctx {
   SweepGeom geom{};
   ChemTotals* d_chem = nullptr;
   double* d_sums = nullptr;
-  double* d_secion = nullptr;
+  double* d_cellrec = nullptr;  // per-cell sweep inputs, rebuilt every iteration (k_cell_records)
   unsigned long long* d_next_cell = nullptr;
   int chem_mode = -1;      // -1 auto, 0 one cell per thread, 1 queue-driven (env C2RAY_CHEM_QUEUE overrides)
   double last_nsub_per_cell = 0.0;  // thermal sub-steps per cell of the previous global pass
@@ -392,11 +393,10 @@ int sweep_all(c2ray_ctx* c) {
     const SweepGeom g = c->geom;
     int rmax = 0;
     for (int d = 0; d < 3; d++) rmax = std::max(rmax, std::max(g.R[d], g.L[d]));
-    if (!c->par.isothermal) {
-      if (!c->d_secion) CK(cudaMalloc(&c->d_secion, 6 * c->N3 * sizeof(double)));
-      LAUNCH(c, k_secion_factors, (unsigned)((c->N3 + 255) / 256), 256, c->xh_av, c->N3, c->d_secion);
-    }
-    GridPtrs G{c->ndens, c->xh_av, c->xhe_av, c->rates, c->d_secion, c->N3, c->lls_type, c->coldensh_LLS, c->d_lls};
+    if (!c->d_cellrec) CK(cudaMalloc(&c->d_cellrec, CELLREC * c->N3 * sizeof(double)));
+    LAUNCH(c, k_cell_records, (unsigned)((c->N3 + 255) / 256), 256, c->ndens, c->xh_av, c->xhe_av, c->N3,
+           c->par.isothermal ? 1 : 0, c->d_cellrec);
+    GridPtrs G{c->d_cellrec, c->rates, c->N3, c->lls_type, c->coldensh_LLS, c->d_lls};
     const int batch = c->par.deterministic ? 1 : c->slots_cap;
     ngroups = c->par.deterministic ? 1 : std::max(1, std::min(c->sweep_groups, std::min(batch, c->n_mine)));
     static const int max_blocks = [] { const char* e = getenv("C2RAY_SWEEP_MAXBLOCKS"); return e ? std::max(1, atoi(e)) : 148 * 16; }();
@@ -816,7 +816,7 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   void* ptrs[] = {c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->rates, c->temp, c->snap_xh,
                   c->snap_xhe, c->snap_temp, c->d_srcpos, c->d_nf, c->d_nfpl, c->d_nfqpl, c->d_tb, c->d_cool,
-                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_secion, c->d_next_cell, c->d_chemred, c->d_clump, c->d_lls, c->d_nbox_all, c->d_srcids_run};
+                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_cellrec, c->d_next_cell, c->d_chemred, c->d_clump, c->d_lls, c->d_nbox_all, c->d_srcids_run};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
   for (int s = 0; s < 3; s++) if (c->packed[s]) cudaFree(c->packed[s]);
@@ -858,7 +858,7 @@ static int pack_tables(c2ray_ctx* c, int s) {
     if (c->packed[s]) { cudaFree(c->packed[s]); c->packed[s] = nullptr; }
     return 0;
   }
-  const size_t n = (size_t)NumFreqBnd * PK_ROWS * PK_ROW;
+  const size_t n = PK_TOTAL;
   if (!c->packed[s]) CK(cudaMalloc(&c->packed[s], n * sizeof(double)));
   const int items = NumFreqBnd * PK_ROWS;
   LAUNCH(c, k_pack_tables, (items + 255) / 256, 256, c->tab[s][0], c->tab[s][1], c->tab[s][2], c->tab[s][3], c->packed[s]);
@@ -1565,6 +1565,45 @@ int c2ray_b200_my_sources(c2ray_ctx* c, int32_t* ids, int32_t cap, int32_t* n) {
   if (!c || !n) return fail(C2RAY_ERR_ARG, "null argument");
   *n = (int32_t)c->my_ids.size();
   if (ids) for (int i = 0; i < *n && i < cap; i++) ids[i] = c->my_ids[i] + 1;
+  return C2RAY_OK;
+}
+
+// mrgrnk.f90:21-215 R_mrgrnk as the reference calls it on the source fluxes (ctrper.f90:108-113): IRNGT(i) = 1-based index
+// of the i-th smallest element, equal keys in their original order (merge sort with `<=` comparisons is stable).
+// A stable LSD radix sort of (key, index) pairs gives the same permutation bit for bit; -0.0 is folded onto +0.0
+// first because Fortran compares them equal while their bit patterns differ.  Off the hot path.
+__global__ void k_mrgrnk_prepare(int n, const float* __restrict__ x, float* __restrict__ key, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  key[i] = v == 0.0f ? 0.0f : v;
+  idx[i] = i + 1;
+}
+
+int c2ray_b200_mrgrnk(c2ray_ctx* c, int32_t n, const float* xvalt, int32_t* irngt) {
+  if (!c || n < 0 || (n > 0 && (!xvalt || !irngt))) return fail(C2RAY_ERR_ARG, "bad argument");
+  if (n == 0) return C2RAY_OK;
+  CK(cudaSetDevice(c->device));
+  float *d_x = nullptr, *d_k0 = nullptr, *d_k1 = nullptr;
+  int *d_i0 = nullptr, *d_i1 = nullptr;
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  auto cleanup = [&]() { for (void* p : {(void*)d_x, (void*)d_k0, (void*)d_k1, (void*)d_i0, (void*)d_i1, d_tmp}) if (p) cudaFree(p); };
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+  ok(cudaMalloc(&d_x, 4 * (size_t)n)) && ok(cudaMalloc(&d_k0, 4 * (size_t)n)) && ok(cudaMalloc(&d_k1, 4 * (size_t)n)) &&
+      ok(cudaMalloc(&d_i0, 4 * (size_t)n)) && ok(cudaMalloc(&d_i1, 4 * (size_t)n)) &&
+      ok(cudaMemcpyAsync(d_x, xvalt, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  if (e == cudaSuccess) {
+    LAUNCH(c, k_mrgrnk_prepare, (n + 255) / 256, 256, n, d_x, d_k0, d_i0);
+    ok(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_k0, d_k1, d_i0, d_i1, n, 0, 32, c->stream)) &&
+        ok(cudaMalloc(&d_tmp, tmp_bytes)) &&
+        ok(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_k0, d_k1, d_i0, d_i1, n, 0, 32, c->stream)) &&
+        ok(cudaMemcpyAsync(irngt, d_i1, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream)) && ok(cudaStreamSynchronize(c->stream));
+    c->launches += 4;
+  }
+  cleanup();
+  if (e != cudaSuccess) return fail(C2RAY_ERR_CUDA, std::string("mrgrnk: ") + cudaGetErrorString(e));
   return C2RAY_OK;
 }
 

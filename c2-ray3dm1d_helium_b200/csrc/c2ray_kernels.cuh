@@ -134,12 +134,15 @@ __global__ void k_decide(Slot* slots, int nslots, SweepGeom g, SweepTotals* tot,
   if (threadIdx.x == 0) tot->nactive = cnt;
 }
 
+// What the sweep reads of a cell, gathered once per iteration into one record per cell (k_cell_records):
+//   [ xh_av(0) ndens , xhe_av(0) ndens , xhe_av(1) ndens , - , y1R(1:3) , y2R(1:3) ]      (fractions floored at epsilon)
+// 80 bytes (isothermal: the first 32).  The x-faces of a shell are strided in memory (i is the fast axis), where ten
+// separate planes cost ten 64-byte DRAM granules per cell; one record costs two.
+constexpr int CELLREC = 10, CELLREC_ISO = 4;
+
 struct GridPtrs {
-  const double* ndens;
-  const double* xh_av;    // (N3,0:1)
-  const double* xhe_av;   // (N3,0:2)
+  const double* cellrec;  // (N3, CELLREC or CELLREC_ISO)
   double* rates;          // phih | phihe0 | phihe1 | phiheat, N3 each
-  const double* secion;   // (N3,6) secondary-ionisation factors y1R(1:3), y2R(1:3) of every cell (non-isothermal)
   size_t N3;
   // Lyman-limit systems (evolve_point.F90:170-180): type_of_LLS 0 none, 1 one column density per cell for the whole
   // mesh, 2 LLS_grid(i,j,k) (material's real array)
@@ -148,13 +151,20 @@ struct GridPtrs {
   const float* lls_grid;
 };
 
-// radiation_photoionrates.f90:557-565 for every cell: depends on xh_av(1) only, so once per iteration, not per source
-__global__ void k_secion_factors(const double* __restrict__ xh_av, size_t N3, double* __restrict__ out) {
+// The cell records.  The secondary-ionisation factors (radiation_photoionrates.f90:557-565) depend on xh_av(1) only, so
+// they are evaluated once per iteration here, not once per source x cell.
+__global__ void k_cell_records(const double* __restrict__ ndens, const double* __restrict__ xh_av,
+                               const double* __restrict__ xhe_av, size_t N3, int iso, double* __restrict__ out) {
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N3) return;
-  const SecIon y = secion_factors_fast(fmax(xh_av[p + N3], epsilon));  // i_state = ion%h_av(1), evolve_point.F90:123,257
-  out[p] = y.y1R0; out[p + N3] = y.y1R1; out[p + 2 * N3] = y.y1R2;
-  out[p + 3 * N3] = y.y2R0; out[p + 4 * N3] = y.y2R1; out[p + 5 * N3] = y.y2R2;
+  const double n = ndens[p];
+  double2* o = reinterpret_cast<double2*>(out + p * (iso ? CELLREC_ISO : CELLREC));
+  o[0] = make_double2(fmax(xh_av[p], epsilon) * n, fmax(xhe_av[p], epsilon) * n);   // evolve_point.F90:117-124
+  o[1] = make_double2(fmax(xhe_av[p + N3], epsilon) * n, 0.0);
+  if (!iso) {
+    const SecIon y = secion_factors_fast(fmax(xh_av[p + N3], epsilon));  // i_state = ion%h_av(1), evolve_point.F90:123,257
+    o[2] = make_double2(y.y1R0, y.y1R1); o[3] = make_double2(y.y1R2, y.y2R0); o[4] = make_double2(y.y2R1, y.y2R2);
+  }
 }
 
 // One shell radius r of every active source.  Work item = (active slot, cell of the shell).
@@ -201,10 +211,8 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
 
     const int i0 = S.s[0], j0 = S.s[1], k0 = S.s[2];
     const size_t p = (size_t)wrap0(i0 + di, m0) + (size_t)m0 * ((size_t)wrap0(j0 + dj, m1) + (size_t)m1 * wrap0(k0 + dk, m2));
-    const double ndens_p = G.ndens[p];
-    const double h_av0 = fmax(G.xh_av[p], epsilon);
-    const double he_av0 = fmax(G.xhe_av[p], epsilon);
-    const double he_av1 = fmax(G.xhe_av[p + G.N3], epsilon);
+    const double2 rec0 = ld2(G.cellrec + p * (ISO ? CELLREC_ISO : CELLREC));      // xh_av(0) n, xhe_av(0) n
+    const double2 rec1 = ld2(G.cellrec + p * (ISO ? CELLREC_ISO : CELLREC) + 2);  // xhe_av(1) n, -
 
     double cin_H, cin_He0, cin_He1, path, vol_ph;
     if (r == 0) {  // evolve_point.F90:140-150
@@ -298,9 +306,9 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
       }
     }
     // evolve_point.F90:237-244
-    const double cout_H = cin_H + h_av0 * ndens_p * path * (1.0 - abu_he);
-    const double cout_He0 = cin_He0 + he_av0 * ndens_p * path * abu_he;
-    const double cout_He1 = cin_He1 + he_av1 * ndens_p * path * abu_he;
+    const double cout_H = cin_H + rec0.x * path * (1.0 - abu_he);
+    const double cout_He0 = cin_He0 + rec0.y * path * abu_he;
+    const double cout_He1 = cin_He1 + rec1.x * path * abu_he;
     if (lane_j == 0) { cur[c] = cout_H; cur[g.cap + c] = cout_He0; cur[2 * g.cap + c] = cout_He1; }
 
     PhotOut phi = {0, 0, 0, 0, 0, 0};
@@ -310,17 +318,22 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
       if (LANES > 1) reduce_bands<ISO, LANES>(A, lane_mask);  // the branch above is uniform over the lanes of a cell
       // the cell's secondary-ionisation factors are only needed now: loading them after the band loop keeps twelve
       // registers free while it runs
+      // (the record's address is formed again from the cell index behind an optimisation barrier, so that only the
+      // index stays live across the loop)
+      size_t p2 = p;
+      asm volatile("" : "+l"(p2));
+      const double* rec = G.cellrec + p2 * (ISO ? CELLREC_ISO : CELLREC);
       SecIon yR = {0, 0, 0, 0, 0, 0};
       if (!iso) {
-        yR.y1R0 = __ldg(G.secion + p); yR.y1R1 = __ldg(G.secion + p + G.N3); yR.y1R2 = __ldg(G.secion + p + 2 * G.N3);
-        yR.y2R0 = __ldg(G.secion + p + 3 * G.N3); yR.y2R1 = __ldg(G.secion + p + 4 * G.N3); yR.y2R2 = __ldg(G.secion + p + 5 * G.N3);
+        const double2 y0 = ld2(rec + 4), y1 = ld2(rec + 6), y2 = ld2(rec + 8);
+        yR.y1R0 = y0.x; yR.y1R1 = y0.y; yR.y1R2 = y1.x; yR.y2R0 = y1.y; yR.y2R1 = y2.x; yR.y2R2 = y2.y;
       }
       phi = photoion_finish<ISO>(A, scale, vol_ph, yR);
-      // the cell's densities again (cache hits) rather than four values held in registers across the band loop
-      const double nd = __ldg(G.ndens + p);
-      phi.photo_HI = fdiv(phi.photo_HI, fmax(__ldg(G.xh_av + p), epsilon) * nd * (1.0 - abu_he));
-      phi.photo_HeI = fdiv(phi.photo_HeI, fmax(__ldg(G.xhe_av + p), epsilon) * nd * abu_he);
-      phi.photo_HeII = fdiv(phi.photo_HeII, fmax(__ldg(G.xhe_av + p + G.N3), epsilon) * nd * abu_he);
+      // the cell's densities again (cache hits) rather than three values held in registers across the band loop
+      const double2 d0 = ld2(rec), d1 = ld2(rec + 2);
+      phi.photo_HI = fdiv(phi.photo_HI, d0.x * (1.0 - abu_he));
+      phi.photo_HeI = fdiv(phi.photo_HeI, d0.y * abu_he);
+      phi.photo_HeII = fdiv(phi.photo_HeII, d1.x * abu_he);
     }
     if (LANES > 1 && lane_j != 0) continue;              // one lane per cell publishes
     atomicAdd(G.rates + p, phi.photo_HI);                // :299-306

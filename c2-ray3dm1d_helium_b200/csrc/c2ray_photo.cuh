@@ -35,6 +35,11 @@ constexpr int PK_ROW = 8;                 // doubles per table position: 4 thick
 constexpr int PK_HALF = 4;                // doubles per packed row (thick rows and thin rows are separate arrays)
 constexpr int PK_ROWS = NumTau + 2;       // rows per band (one duplicate at the end)
 constexpr size_t PK_THIN_OFF = (size_t)NumFreqBnd * PK_ROWS * PK_HALF;  // the thin rows follow all thick rows
+// isothermal runs read no heating values: a third copy holds photo_thick alone (8 bytes per table position, four
+// times as many positions per cache line), then photo_thin alone
+constexpr size_t PK_ISO_OFF = 2 * PK_THIN_OFF;
+constexpr size_t PK_ISO_THIN_OFF = PK_ISO_OFF + (size_t)NumFreqBnd * PK_ROWS;
+constexpr size_t PK_TOTAL = PK_ISO_THIN_OFF + (size_t)NumFreqBnd * PK_ROWS;  // doubles per SED
 
 // column_density.f90:351-376 with the fast reciprocal
 __device__ __forceinline__ double weightf_fast(double cd, double sig) { return fast_rcp(fmax(0.6, cd * sig)); }
@@ -53,6 +58,7 @@ __device__ __forceinline__ TauPos tau_table_position(double tau) {
   return p;
 }
 
+// (ld.global.nc.L1::evict_last on these loads was tried: no change at 16 sources, 8 % slower at 1000 -- profiles/README.md)
 __device__ __forceinline__ double2 ld2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ double lerp(double a, double b, double t) { return fma(b - a, t, a); }  // :321-324
 
@@ -107,7 +113,7 @@ struct CellCols {
 // One frequency band (1-based b, NSP species absorb in it) for every active SED.
 // MULTI = false: only the black-body SED exists in this run; NFlux is then factored out of the band loop.
 template <bool ISO, int NSP, bool MULTI>
-__device__ __forceinline__ void band_step(int b, const CellCols& c, const double nflux[3], const bool act[3],
+__device__ __forceinline__ void band_step(int b, const CellCols& c, const double nflux[3], unsigned actmask,
                                           PhotAcc& A) {
   const int q = b - 1;
   const double sHI = d_band.sigma_HI[q];
@@ -137,13 +143,33 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
   double ph_HI = 0.0, ph_HeI = 0.0, ph_HeII = 0.0;    // heating per species of this band, all SEDs
   const size_t row_in = ((size_t)q * PK_ROWS + pin.ipos) * PK_HALF;
   const size_t row_out = ((size_t)q * PK_ROWS + pout.ipos) * PK_HALF;
+  // (a rolled loop over the SEDs was tried for the MULTI kernels: fewer registers, but 8 % slower at 4 CTAs/SM and
+  // 27 % slower at 5 -- profiles/README.md)
 #pragma unroll
   for (int s = 0; s < (MULTI ? 3 : 1); s++) {
     if (MULTI) {
-      if (!act[s] || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
+      if (!((actmask >> s) & 1u) || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
     }
     const double* __restrict__ pk = d_run.sed[s].packed;
     const double NFlux = MULTI ? nflux[s] : 1.0;
+    if (ISO) {  // photo_lookuptable :390-425 on the photo-only copy of the tables
+      const double* pi = pk + PK_ISO_OFF + (size_t)q * PK_ROWS + pin.ipos;
+      const double phi_in = NFlux * lerp(__ldg(pi), __ldg(pi + 1), pin.residual);
+      double phi_all, phi_out;
+      if (thick_p) {
+        const double* po = pk + PK_ISO_OFF + (size_t)q * PK_ROWS + pout.ipos;
+        phi_out = NFlux * lerp(__ldg(po), __ldg(po + 1), pout.residual);
+        phi_all = phi_in - phi_out;
+      } else {
+        const double* pt = pi + (PK_ISO_THIN_OFF - PK_ISO_OFF);
+        phi_all = NFlux * dtau * lerp(__ldg(pt), __ldg(pt + 1), pin.residual);
+        phi_out = phi_in - phi_all;
+      }
+      A.a_in += phi_in;
+      A.a_out += phi_out;
+      phot += phi_all;
+      continue;
+    }
     const double* ri = pk + row_in;
     const double* ro = pk + row_out;
     const double* ti = ri + PK_THIN_OFF;  // thin rows at tau_in
@@ -222,7 +248,7 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
   c.in_HI = in_HI; c.in_HeI = in_HeI; c.in_HeII = in_HeII;
   c.out_HI = out_HI; c.out_HeI = out_HeI; c.out_HeII = out_HeII;
   c.cell_HI = out_HI - in_HI; c.cell_HeI = out_HeI - in_HeI; c.cell_HeII = out_HeII - in_HeII;  // :167-169
-  bool act[3] = {true, false, false};
+  unsigned act = 1u;  // bit s: SED s exists and this source emits in it
   int blo, bhi;
   double scale = 1.0;
   unsigned long long bands = ~0ull;  // bit b-1: some active SED covers band b (BB and QPL ranges can leave a gap)
@@ -230,8 +256,10 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
     blo = NumFreqBnd + 1; bhi = 0; bands = 0ull;
 #pragma unroll
     for (int s = 0; s < 3; s++) {
-      act[s] = (d_run.sed[s].hi >= d_run.sed[s].lo) && (nflux[s] > 0.0);
-      if (act[s]) {
+      const bool on = (d_run.sed[s].hi >= d_run.sed[s].lo) && (nflux[s] > 0.0);
+      if (s == 0) act = 0u;
+      if (on) {
+        act |= 1u << s;
         blo = min(blo, d_run.sed[s].lo); bhi = max(bhi, d_run.sed[s].hi);
         bands |= (~0ull >> (64 - d_run.sed[s].hi)) & (~0ull << (d_run.sed[s].lo - 1));
       }
@@ -321,6 +349,8 @@ __global__ void k_pack_tables(const double* __restrict__ photo_thick, const doub
     packed[(size_t)t * PK_HALF + k] = v[k];
     packed[PK_THIN_OFF + (size_t)t * PK_HALF + k] = v[PK_HALF + k];
   }
+  packed[PK_ISO_OFF + t] = v[0];
+  packed[PK_ISO_THIN_OFF + t] = v[PK_HALF];
 }
 
 }  // namespace c2

@@ -305,6 +305,13 @@ class C2Ray:
                                                      _p(_f64(coldensh_out)), _p(_f64(coldenshe_out)), _p(out)))
         return out
 
+    def mrgrnk(self, xvalt):
+        """mrgrnk.f90: rank (1-based argsort, stable) of a real(si) array, on the device."""
+        x = np.ascontiguousarray(xvalt, dtype=np.float32)
+        out = np.zeros(len(x), dtype=np.int32)
+        capi.check(self.lib.c2ray_b200_mrgrnk(self.ctx, C.c_int32(len(x)), _p(x), _p(out)))
+        return out
+
     # -- multi-GPU ----------------------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id():

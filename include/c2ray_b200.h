@@ -209,6 +209,11 @@ int c2ray_b200_fortran_records_write(const char* path, int32_t n, const void* co
                                      int64_t max_subrecord);
 int c2ray_b200_fortran_records_read(const char* path, int32_t n, void* const* data, const int64_t* bytes);
 
+/* mrgrnk.f90 R_mrgrnk(XVALT, IRNGT) as ctrper.f90:108-113 uses it: irngt[i] = 1-based position of the (i+1)-th smallest
+ * key, equal keys in input order.  Bit-exact against the merge sort; off the hot path (the reference computes the
+ * source permutation but never uses it, evolve_source.F90:88-90). */
+int c2ray_b200_mrgrnk(c2ray_ctx* ctx, int32_t n, const float* xvalt, int32_t* irngt);
+
 /* ---- multi-GPU (mpi.F90 my_mpi: rank, npr ; evolve.F90:505-548 allreduce) ---------------------------- */
 /* 128-byte NCCL unique id created on rank 0 and broadcast by the host (MPI_BCAST / torch.distributed). */
 int c2ray_b200_comm_unique_id(uint8_t id[128]);

@@ -1,11 +1,12 @@
 """One global iteration (RT pass over all sources + global chemistry pass) of BASELINE configs[1] -- the command the
-ncu captures under profiles/ are taken from.  usage: profile_step.py [mesh] [iterations]"""
+ncu captures under profiles/ are taken from.  usage: profile_step.py [mesh] [iterations] [iso]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import c2ray_b200
 mesh = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-p = c2ray_b200.synth.make_problem(2, n=mesh, num_src=16, isothermal=False)
+iso = len(sys.argv) > 3 and sys.argv[3] == "iso"
+p = c2ray_b200.synth.make_problem(2, n=mesh, num_src=16, isothermal=iso)
 c = c2ray_b200.from_problem(p, device=0)
 c.begin_step()
 for it in range(iters):
