@@ -168,14 +168,14 @@ __global__ void k_cell_records(const double* __restrict__ ndens, const double* _
 }
 
 // One shell radius r of every active source.  Work item = (active slot, cell of the shell).
-// Resident CTAs per SM: with the secondary-ionisation factors out of the band loop the single-SED kernels fit 96
-// registers with a 12..28-byte spill and gain 3 % from the fifth CTA (A/B on one box: 17.86 -> 17.31 ms per pass); the
-// multi-SED kernels would spill 164 bytes and stay at 4.
+// Resident CTAs per SM: with the secondary-ionisation factors out of the band loop the kernels fit 96 registers with
+// a spill of a few words and gain 3-4 % from the fifth CTA (A/B on one box: 17.86 -> 17.31 ms per pass at 16 sources,
+// 615 -> 592 ms at 1000 sources with the multi-SED kernel); a sixth (80 registers) loses 1 %.
 #ifndef C2RAY_SWEEP_MINBLOCKS
 #define C2RAY_SWEEP_MINBLOCKS 5
 #endif
 #ifndef C2RAY_SWEEP_MINBLOCKS_MULTI
-#define C2RAY_SWEEP_MINBLOCKS_MULTI 4
+#define C2RAY_SWEEP_MINBLOCKS_MULTI 5
 #endif
 // LANES (1 or a power of two <= 32): lanes of a warp that share one cell, each taking every LANES-th frequency band.
 // One update is a dependent chain of ~9 k instructions, ~25 us for a warp on its own; a launch that cannot fill the

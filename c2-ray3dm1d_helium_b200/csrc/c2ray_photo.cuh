@@ -114,7 +114,7 @@ struct CellCols {
 // MULTI = false: only the black-body SED exists in this run; NFlux is then factored out of the band loop.
 template <bool ISO, int NSP, bool MULTI>
 __device__ __forceinline__ void band_step(int b, const CellCols& c, const double nflux[3], unsigned actmask,
-                                          PhotAcc& A) {
+                                          PhotAcc& A, const double* __restrict__ pk_single = nullptr) {
   const int q = b - 1;
   const double sHI = d_band.sigma_HI[q];
   const double sHeI = NSP >= 2 ? d_band.sigma_HeI[q] : 0.0;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
     if (MULTI) {
       if (!((actmask >> s) & 1u) || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
     }
-    const double* __restrict__ pk = d_run.sed[s].packed;
+    const double* __restrict__ pk = MULTI ? d_run.sed[s].packed : (pk_single ? pk_single : d_run.sed[0].packed);
     const double NFlux = MULTI ? nflux[s] : 1.0;
     if (ISO) {  // photo_lookuptable :390-425 on the photo-only copy of the tables
       const double* pi = pk + PK_ISO_OFF + (size_t)q * PK_ROWS + pin.ipos;
@@ -248,6 +248,38 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
   c.in_HI = in_HI; c.in_HeI = in_HeI; c.in_HeII = in_HeII;
   c.out_HI = out_HI; c.out_HeI = out_HeI; c.out_HeII = out_HeII;
   c.cell_HI = out_HI - in_HI; c.cell_HeI = out_HeI - in_HeI; c.cell_HeII = out_HeII - in_HeII;  // :167-169
+#ifndef C2RAY_MULTI_SED_INNER
+  if (MULTI) {
+    // Every rate is linear in the SEDs' contributions and the optical depths do not depend on the SED, so a source
+    // with several SEDs is traced as the sum of single-SED sources: for each SED that the source emits in, the lean
+    // single-SED band loop over that SED's own band range (NormFlux factored out), then one multiply-add per
+    // accumulator.  The reference's order -- sum over the SEDs inside every band (:390-456) -- costs predicated
+    // copies of the table look-ups in every band for a sum that usually has one term (the black body ends at band
+    // 33-36, PL / QPL start at 38).
+    PhotAcc T = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int s = 0; s < 3; s++) {
+      const int lo = d_run.sed[s].lo, hi = d_run.sed[s].hi;
+      const double nf = nflux[s];
+      if (hi < lo || !(nf > 0.0)) continue;
+      const double* __restrict__ pk = d_run.sed[s].packed;
+      PhotAcc B = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      if (lo <= NumBndin1 && lane_j == 0) band_step<ISO, 1, false>(1, c, nflux, 1u, B, pk);
+      for (int b = max(lo, NumBndin1 + 1) + lane_j; b <= min(hi, NumBndin1 + NumBndin2); b += LANES)
+        band_step<ISO, 2, false>(b, c, nflux, 1u, B, pk);
+      for (int b = max(lo, NumBndin1 + NumBndin2 + 1) + lane_j; b <= hi; b += LANES)
+        band_step<ISO, 3, false>(b, c, nflux, 1u, B, pk);
+      T.a_in = fma(nf, B.a_in, T.a_in); T.a_out = fma(nf, B.a_out, T.a_out);
+      T.a_HI = fma(nf, B.a_HI, T.a_HI); T.a_HeI = fma(nf, B.a_HeI, T.a_HeI); T.a_HeII = fma(nf, B.a_HeII, T.a_HeII);
+      if (!ISO) {
+        T.f_heat = fma(nf, B.f_heat, T.f_heat);
+        T.s1 = fma(nf, B.s1, T.s1); T.s2 = fma(nf, B.s2, T.s2); T.s3 = fma(nf, B.s3, T.s3); T.s4 = fma(nf, B.s4, T.s4);
+      }
+    }
+    scale_out = 1.0;
+    return T;
+  }
+#endif
   unsigned act = 1u;  // bit s: SED s exists and this source emits in it
   int blo, bhi;
   double scale = 1.0;
