@@ -211,26 +211,26 @@ int bind(c2ray_ctx* c) {
 }
 
 int upload_band_const(c2ray_ctx* c) {
-  static BandConst bc;
-  memset(&bc, 0, sizeof(bc));
-  bc.sigma_HI[0] = sigma_HI_at_ion_freq;  // radiation_sizes.f90:381-383
+  static BandRec bc[NumFreqBnd];
+  memset(bc, 0, sizeof(bc));
+  bc[0].sigma_HI = sigma_HI_at_ion_freq;  // radiation_sizes.f90:381-383
   for (int i = 0; i < 26; i++) {
     const int q = NumBndin1 + i;
-    bc.sigma_HI[q] = BD_SIGMA_HI_B2[i]; bc.sigma_HeI[q] = BD_SIGMA_HEI_B2[i]; bc.sigma_HeII[q] = 0.0;
-    bc.f1ion_HI[q] = BD_F1ION_HI_B2[i]; bc.f1ion_HeI[q] = BD_F1ION_HEI_B2[i]; bc.f1ion_HeII[q] = BD_F1ION_HEII_B2[i];
-    bc.f2ion_HI[q] = BD_F2ION_HI_B2[i]; bc.f2ion_HeI[q] = BD_F2ION_HEI_B2[i]; bc.f2ion_HeII[q] = BD_F2ION_HEII_B2[i];
-    bc.f1heat_HI[q] = BD_F1HEAT_HI_B2[i]; bc.f1heat_HeI[q] = BD_F1HEAT_HEI_B2[i]; bc.f1heat_HeII[q] = BD_F1HEAT_HEII_B2[i];
-    bc.f2heat_HI[q] = BD_F2HEAT_HI_B2[i]; bc.f2heat_HeI[q] = BD_F2HEAT_HEI_B2[i]; bc.f2heat_HeII[q] = BD_F2HEAT_HEII_B2[i];
+    bc[q].sigma_HI = BD_SIGMA_HI_B2[i]; bc[q].sigma_HeI = BD_SIGMA_HEI_B2[i]; bc[q].sigma_HeII = 0.0;
+    bc[q].f1ion_HI = BD_F1ION_HI_B2[i]; bc[q].f1ion_HeI = BD_F1ION_HEI_B2[i]; bc[q].f1ion_HeII = BD_F1ION_HEII_B2[i];
+    bc[q].f2ion_HI = BD_F2ION_HI_B2[i]; bc[q].f2ion_HeI = BD_F2ION_HEI_B2[i]; bc[q].f2ion_HeII = BD_F2ION_HEII_B2[i];
+    bc[q].f1heat_HI = BD_F1HEAT_HI_B2[i]; bc[q].f1heat_HeI = BD_F1HEAT_HEI_B2[i]; bc[q].f1heat_HeII = BD_F1HEAT_HEII_B2[i];
+    bc[q].f2heat_HI = BD_F2HEAT_HI_B2[i]; bc[q].f2heat_HeI = BD_F2HEAT_HEI_B2[i]; bc[q].f2heat_HeII = BD_F2HEAT_HEII_B2[i];
   }
   for (int i = 0; i < 20; i++) {
     const int q = NumBndin1 + NumBndin2 + i;
-    bc.sigma_HI[q] = BD_SIGMA_HI_B3[i]; bc.sigma_HeI[q] = BD_SIGMA_HEI_B3[i]; bc.sigma_HeII[q] = BD_SIGMA_HEII_B3[i];
-    bc.f1ion_HI[q] = BD_F1ION_HI_B3[i]; bc.f1ion_HeI[q] = BD_F1ION_HEI_B3[i]; bc.f1ion_HeII[q] = BD_F1ION_HEII_B3[i];
-    bc.f2ion_HI[q] = BD_F2ION_HI_B3[i]; bc.f2ion_HeI[q] = BD_F2ION_HEI_B3[i]; bc.f2ion_HeII[q] = BD_F2ION_HEII_B3[i];
-    bc.f1heat_HI[q] = BD_F1HEAT_HI_B3[i]; bc.f1heat_HeI[q] = BD_F1HEAT_HEI_B3[i]; bc.f1heat_HeII[q] = BD_F1HEAT_HEII_B3[i];
-    bc.f2heat_HI[q] = BD_F2HEAT_HI_B3[i]; bc.f2heat_HeI[q] = BD_F2HEAT_HEI_B3[i]; bc.f2heat_HeII[q] = BD_F2HEAT_HEII_B3[i];
+    bc[q].sigma_HI = BD_SIGMA_HI_B3[i]; bc[q].sigma_HeI = BD_SIGMA_HEI_B3[i]; bc[q].sigma_HeII = BD_SIGMA_HEII_B3[i];
+    bc[q].f1ion_HI = BD_F1ION_HI_B3[i]; bc[q].f1ion_HeI = BD_F1ION_HEI_B3[i]; bc[q].f1ion_HeII = BD_F1ION_HEII_B3[i];
+    bc[q].f2ion_HI = BD_F2ION_HI_B3[i]; bc[q].f2ion_HeI = BD_F2ION_HEI_B3[i]; bc[q].f2ion_HeII = BD_F2ION_HEII_B3[i];
+    bc[q].f1heat_HI = BD_F1HEAT_HI_B3[i]; bc[q].f1heat_HeI = BD_F1HEAT_HEI_B3[i]; bc[q].f1heat_HeII = BD_F1HEAT_HEII_B3[i];
+    bc[q].f2heat_HI = BD_F2HEAT_HI_B3[i]; bc[q].f2heat_HeI = BD_F2HEAT_HEI_B3[i]; bc[q].f2heat_HeII = BD_F2HEAT_HEII_B3[i];
   }
-  CK(cudaMemcpyToSymbol(d_band, &bc, sizeof(bc)));
+  CK(cudaMemcpyToSymbol(d_band, bc, sizeof(bc)));
   return 0;
 }
 

@@ -43,12 +43,17 @@ struct SedDev {
   double S_star;
 };
 
-struct BandConst {  // radiation_sizes.f90 arrays, 0-based band index
-  double sigma_HI[NumFreqBnd], sigma_HeI[NumFreqBnd], sigma_HeII[NumFreqBnd];
-  double f1ion_HI[NumFreqBnd], f1ion_HeI[NumFreqBnd], f1ion_HeII[NumFreqBnd];
-  double f2ion_HI[NumFreqBnd], f2ion_HeI[NumFreqBnd], f2ion_HeII[NumFreqBnd];
-  double f1heat_HI[NumFreqBnd], f1heat_HeI[NumFreqBnd], f1heat_HeII[NumFreqBnd];
-  double f2heat_HI[NumFreqBnd], f2heat_HeI[NumFreqBnd], f2heat_HeII[NumFreqBnd];
+// radiation_sizes.f90 band arrays, one 128-byte record per band (0-based band index): a band step reads up to 15 of
+// these through dynamically indexed constant loads, and one or two constant-cache lines per band serve them where 15
+// separate arrays cost 15 lines (the LDC waits showed up as "short scoreboard" stalls: 13 % of the samples at 16
+// sources, 24 % at 1000)
+struct BandRec {
+  double sigma_HI, sigma_HeI, sigma_HeII;
+  double f1ion_HI, f1ion_HeI, f1ion_HeII;
+  double f2ion_HI, f2ion_HeI, f2ion_HeII;
+  double f1heat_HI, f1heat_HeI, f1heat_HeII;
+  double f2heat_HI, f2heat_HeI, f2heat_HeII;
+  double pad;
 };
 
 struct RunConst {
@@ -64,7 +69,7 @@ struct RunConst {
   int mesh[3];
 };
 
-__constant__ BandConst d_band;
+__constant__ BandRec d_band[NumFreqBnd];
 __constant__ RunConst d_run;
 
 struct RecCol {

@@ -39,6 +39,31 @@ def run(p, local, uid, rank, world, split, steps, schedule=0):
     return hist, out + (mine,)
 
 
+def run_dump_restart(p, local, uid_fn, rank, world, tmpdir):
+    """Split pass + iteration dumps after every source pass (rank 0 writes), then a fresh set of contexts resumes from
+    the last-but-one dump: must end bitwise where the uninterrupted run ended (deterministic sweeps, one chemistry kernel)."""
+    os.environ["C2RAY_SPLIT_CHEM"] = "1"
+    os.environ["C2RAY_CHEM_QUEUE"] = "0"
+    c = c2ray_b200.from_problem(p, device=local, deterministic=True)
+    c.comm_init(uid_fn(), rank, world)
+    c.set_dump(tmpdir + "/", 0.0)
+    st = c.evolve3D(0.0, p["dt"], 0)
+    ref = c.get_state() + tuple(c.get_rates())
+    c.close()
+    dist.barrier()
+    last = st["niter"]
+    which = 1 if (last - 1) % 2 == 1 else 2
+    c = c2ray_b200.from_problem(p, device=local, deterministic=True)
+    c.comm_init(uid_fn(), rank, world)
+    c.set_dump(tmpdir + "/", -1.0)
+    st2 = c.evolve3D(0.0, p["dt"], which)
+    out = c.get_state() + tuple(c.get_rates())
+    c.close()
+    os.environ.pop("C2RAY_CHEM_QUEUE")
+    same = st2["niter"] == last and all(np.array_equal(a, b) for a, b in zip(out, ref))
+    return same, last
+
+
 def relerr(a, b):
     return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-300)))
 
@@ -66,7 +91,11 @@ def main():
     h_bal, s_bal = run(p, local, uid(), rank, world, True, steps, schedule=1)
     mine_static, mine_bal = s_split[-1], s_bal[-1]
     s_split, s_repl, s_one, s_bal = s_split[:-1], s_repl[:-1], s_one[:-1], s_bal[:-1]
-    ok = True
+    import tempfile
+    tmp = [tempfile.mkdtemp(prefix="c2ray_dump_") if rank == 0 else None]
+    dist.broadcast_object_list(tmp, src=0)
+    restart_ok, restart_niter = run_dump_restart(p, local, uid, rank, world, tmp[0])
+    ok = restart_ok
     # the balanced schedule: same integer histories, same fields to summation order, every source dealt exactly once
     counts = torch.zeros(len(p["NormFlux"]) + 1, dtype=torch.int32, device="cuda")
     counts[torch.tensor(mine_bal, dtype=torch.long, device="cuda")] += 1
@@ -105,7 +134,8 @@ def main():
     print(f"rank {rank}/{world}: mesh {mesh} sources {nsrc} niter {[h[0] for h in h_split]} split-vs-replicated {e_sr:.2e} "
           f"(tol {tol_sr:g}) vs-one-rank err/tol {max(errs.values()):.3f} all-ranks-equal {same} | ms sweep/chem/comm split "
           f"{ms(h_split)[0]:.1f}/{ms(h_split)[1]:.1f}/{ms(h_split)[2]:.1f} replicated {ms(h_repl)[0]:.1f}/{ms(h_repl)[1]:.1f}/{ms(h_repl)[2]:.1f}"
-          f" | balanced schedule: sources {mine_static} -> {mine_bal}, err/tol {e_bal:.3f}"
+          f" | balanced schedule: sources {[int(x) for x in mine_static]} -> {[int(x) for x in mine_bal]}, err/tol {e_bal:.3f}"
+          f" | dump+restart under the split pass (niter {restart_niter}) bitwise {restart_ok}"
           f" -> {'OK' if ok else 'MISMATCH'}", flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
