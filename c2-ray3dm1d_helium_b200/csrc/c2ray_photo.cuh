@@ -31,6 +31,10 @@
 
 namespace c2 {
 
+// (the band records in shared memory instead of constant memory: 5 % slower at 16 sources, 5 % faster at 1000 --
+// profiles/README.md)
+#define BANDREC(q) d_band[q]
+
 constexpr int PK_ROW = 8;                 // doubles per table position: 4 thick + 4 thin values
 constexpr int PK_HALF = 4;                // doubles per packed row (thick rows and thin rows are separate arrays)
 constexpr int PK_ROWS = NumTau + 2;       // rows per band (one duplicate at the end)
@@ -116,9 +120,9 @@ template <bool ISO, int NSP, bool MULTI>
 __device__ __forceinline__ void band_step(int b, const CellCols& c, const double nflux[3], unsigned actmask,
                                           PhotAcc& A, const double* __restrict__ pk_single = nullptr) {
   const int q = b - 1;
-  const double sHI = d_band[q].sigma_HI;
-  const double sHeI = NSP >= 2 ? d_band[q].sigma_HeI : 0.0;
-  const double sHeII = NSP == 3 ? d_band[q].sigma_HeII : 0.0;
+  const double sHI = BANDREC(q).sigma_HI;
+  const double sHeI = NSP >= 2 ? BANDREC(q).sigma_HeI : 0.0;
+  const double sHeII = NSP == 3 ? BANDREC(q).sigma_HeII : 0.0;
   double tau_in = c.in_HI * sHI, tau_out = c.out_HI * sHI;             // :172-183
   if (NSP >= 2) { tau_in = fma(c.in_HeI, sHeI, tau_in); tau_out = fma(c.out_HeI, sHeI, tau_out); }
   if (NSP == 3) { tau_in = fma(c.in_HeII, sHeII, tau_in); tau_out = fma(c.out_HeII, sHeII, tau_out); }
@@ -219,15 +223,15 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
     // (:654-669, :739-759)
     double df_heat = ph_HI + ph_HeI + ph_HeII;
     if (NSP >= 2) {
-      double fs1 = d_band[q].f1ion_HI * ph_HI + d_band[q].f1ion_HeI * ph_HeI;
-      double fs2 = d_band[q].f2ion_HI * ph_HI + d_band[q].f2ion_HeI * ph_HeI;
-      double fs3 = d_band[q].f1heat_HI * ph_HI + d_band[q].f1heat_HeI * ph_HeI;
-      double fs4 = d_band[q].f2heat_HI * ph_HI + d_band[q].f2heat_HeI * ph_HeI;
+      double fs1 = BANDREC(q).f1ion_HI * ph_HI + BANDREC(q).f1ion_HeI * ph_HeI;
+      double fs2 = BANDREC(q).f2ion_HI * ph_HI + BANDREC(q).f2ion_HeI * ph_HeI;
+      double fs3 = BANDREC(q).f1heat_HI * ph_HI + BANDREC(q).f1heat_HeI * ph_HeI;
+      double fs4 = BANDREC(q).f2heat_HI * ph_HI + BANDREC(q).f2heat_HeI * ph_HeI;
       if (NSP == 3) {
-        fs1 = fma(d_band[q].f1ion_HeII, ph_HeII, fs1);
-        fs2 = fma(d_band[q].f2ion_HeII, ph_HeII, fs2);
-        fs3 = fma(d_band[q].f1heat_HeII, ph_HeII, fs3);
-        fs4 = fma(d_band[q].f2heat_HeII, ph_HeII, fs4);
+        fs1 = fma(BANDREC(q).f1ion_HeII, ph_HeII, fs1);
+        fs2 = fma(BANDREC(q).f2ion_HeII, ph_HeII, fs2);
+        fs3 = fma(BANDREC(q).f1heat_HeII, ph_HeII, fs3);
+        fs4 = fma(BANDREC(q).f2heat_HeII, ph_HeII, fs4);
       }
       A.s1 += fs1; A.s2 += fs2; A.s3 += fs3; A.s4 += fs4;
     }
