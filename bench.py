@@ -33,10 +33,11 @@ UNIT = "updates/s"
 SRC_PER_GPU = 16
 MESH = 128
 BYTES_PER_UPDATE = 104  # 5 FP64 state reads + read-modify-write of 4 rate grids (thermal)
-# DRAM traffic of k_sweep_shell from the committed `ncu --set full` capture (profiles/r1_ncu_full_final_sweep_chem_128.csv,
-# launch at shell radius 56: dram__bytes_read.sum + dram__bytes_write.sum = 582.3 + 86.1 MB for 1,204,256 updates)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 668.5e6
-NCU_TRAFFIC_BYTES_PER_UPDATE = 555.0
+# DRAM traffic of k_sweep_shell from the committed `ncu --set full` capture (profiles/r1_ncu_full_kernels_v3_128.csv,
+# first launch = one stream group (8 sources) at shell radius 56: dram__bytes_read.sum + dram__bytes_write.sum =
+# 118.9 + 21.2 MB for 8 x 75,266 = 602,128 updates)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 140.1e6
+NCU_TRAFFIC_BYTES_PER_UPDATE = 232.7
 
 
 def workload(n_gpus, mesh):
@@ -253,9 +254,9 @@ def run_b200(args):
         sweep_gbs = BYTES_PER_UPDATE * upd_local / (ms_sweep * 1e-3) / 1e9
         fp64 = c.measure_fp64()
         roofline = {"kernel": "k_sweep_shell", "bound": "hbm", "achieved": sweep_gbs, "peak": peak, "unit": "GB/s",
-                    "frac": sweep_gbs / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_note": "ncu capture of the r=56 launch (1.2 M updates): "
-                    f"{NCU_TRAFFIC_BYTES_PER_UPDATE:.0f} B/update measured vs {BYTES_PER_UPDATE} B algorithmic (strided x-face sectors, "
-                    "48 B of precomputed secondary-ionisation factors, rate-grid atomics)", "peak_source": peak_src,
+                    "frac": sweep_gbs / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_note": "ncu capture of one r=56 launch (602 k updates): "
+                    f"{NCU_TRAFFIC_BYTES_PER_UPDATE:.0f} B/update measured vs {BYTES_PER_UPDATE} B algorithmic (64-byte DRAM granules on the strided "
+                    "x-faces of a shell for the 80-byte cell records and the rate-grid atomics; shell scratch)", "peak_source": peak_src,
                     "launches": int(launches), "avg_launch_ms": ms_sweep / max(1, sum(s["niter"] for s in stats)) ,
                     "note": "the sweep is FP64/LSU bound, not HBM bound (SURVEY F6): see fp64 fields",
                     "updates_per_s_kernel": upd_local / (ms_sweep * 1e-3), "fp64_peak_tflops_measured": fp64,
