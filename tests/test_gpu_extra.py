@@ -218,3 +218,19 @@ def test_band_split_and_plain_sweep_kernels_agree(monkeypatch):
         assert np.array_equal(a != 0, o != 0) and np.array_equal(b != 0, o != 0)
         assert relerr(a, b, 1e-300) < 1e-12
         assert relerr(a, o, 1e-300) < 1e-8 and relerr(b, o, 1e-300) < 1e-8
+
+
+def test_mrgrnk_on_the_device_is_bit_exact():
+    """mrgrnk.f90 (ctrper.f90:108-113 ranks the source fluxes with it): 1-based stable argsort of real(si) keys."""
+    rng = np.random.default_rng(12)
+    c = c2ray_b200.C2Ray([8, 8, 8])
+    for n in (1, 2, 17, 1000, 100003):
+        x = rng.standard_normal(n).astype(np.float32)
+        x[rng.integers(0, n, n // 3)] = np.float32(0.5)       # ties
+        x[rng.integers(0, n, max(1, n // 50))] = np.float32(-0.0)  # Fortran: -0.0 == +0.0, stable order between them
+        x[rng.integers(0, n, max(1, n // 50))] = np.float32(0.0)
+        got = c.mrgrnk(x)
+        assert np.array_equal(got, np.argsort(x, kind="stable") + 1), n
+        assert np.array_equal(got, O.mrgrnk(x)), n
+    assert c.mrgrnk(np.zeros(0, dtype=np.float32)).size == 0
+    c.close()
