@@ -54,8 +54,9 @@ struct TauPos { int ipos; double residual; };
 // With tau >= 1e-20 the lower clamp never binds; the upper one is applied to the integer index: for odpos > NumTau
 // both interpolation rows are row NumTau, so the residual is irrelevant.
 __device__ __forceinline__ TauPos tau_table_position(double tau) {
-  const double lt = fast_log10(fmax(1.0e-20, tau));
-  const double odpos = fma(lt - minlogtau, 1.0 / dlogtau, 1.0);
+  static_assert(minlogtau == -20.0 && dlogtau == 24.0 / 2000.0, "d_lit[6] holds 1/dlogtau");
+  const double lt = fast_log10(fmax(d_lit[3], tau));
+  const double odpos = fma(lt - minlogtau, d_lit[6], 1.0);
   TauPos p;
   p.ipos = min((int)odpos, NumTau);
   p.residual = odpos - (double)p.ipos;
@@ -127,8 +128,8 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
   if (NSP >= 2) { tau_in = fma(c.in_HeI, sHeI, tau_in); tau_out = fma(c.out_HeI, sHeI, tau_out); }
   if (NSP == 3) { tau_in = fma(c.in_HeII, sHeII, tau_in); tau_out = fma(c.out_HeII, sHeII, tau_out); }
   const double dtau = tau_out - tau_in;
-  const bool thick_p = fabs(dtau) > tau_photo_limit;
-  const bool thick_h = fabs(dtau) > tau_heat_limit;
+  const bool thick_p = fabs(dtau) > d_lit[4];  // tau_photo_limit, :342
+  const bool thick_h = fabs(dtau) > d_lit[5];  // tau_heat_limit, :482
   // both positions unconditionally: the two log10 evaluations are independent and interleave (the thin branch, which
   // does not need pout, is the rare one)
   const TauPos pin = tau_table_position(tau_in);
