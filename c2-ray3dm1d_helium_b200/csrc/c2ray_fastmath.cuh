@@ -73,26 +73,30 @@ __device__ __forceinline__ double fast_log10(double x) {
 __device__ __forceinline__ double fast_log(double x) {
   int e;
   const double l = log_core(x, e);
-  return fma((double)e, 0.69314718055994530942, l + l);
+  return fma((double)e, d_lit[2], l + l);
 }
 
 // exp(x) for |x| <= ~700 (clamped below at -700: exp(-700) ~ 1e-304 stands in for 0): k = rint(x/ln2),
 // r = x - k ln2 (two-word ln2), degree-13 Taylor polynomial on |r| <= 0.347 (truncation 5e-18), scale by 2^k
+// [0] log2(e)  [1],[2] -ln2 in two words  [3..14] 1/2! .. 1/13! (constant-bank operands, see d_lit)
+__constant__ double d_expc[15] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+                                  0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0,
+                                  1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0, 1.0 / 479001600.0, 1.0 / 6227020800.0};
 __device__ __forceinline__ double fast_exp(double x) {
   x = fmax(x, -700.0);
-  const double kf = rint(x * 1.4426950408889634074);
-  double r = fma(kf, -6.93147180369123816490e-01, x);
-  r = fma(kf, -1.90821492927058770002e-10, r);
+  const double kf = rint(x * d_expc[0]);
+  double r = fma(kf, d_expc[1], x);
+  r = fma(kf, d_expc[2], r);
   // Estrin on 1 + r + r^2/2! + ... + r^13/13!
   const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
   const double p0 = fma(r, 1.0, 1.0);
-  const double p1 = fma(r, 1.0 / 6.0, 0.5);
-  const double p2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  const double p3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-  const double p4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
-  const double p5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+  const double p1 = fma(r, d_expc[4], d_expc[3]);
+  const double p2 = fma(r, d_expc[6], d_expc[5]);
+  const double p3 = fma(r, d_expc[8], d_expc[7]);
+  const double p4 = fma(r, d_expc[10], d_expc[9]);
+  const double p5 = fma(r, d_expc[12], d_expc[11]);
   const double q0 = fma(p1, r2, p0), q1 = fma(p3, r2, p2), q2 = fma(p5, r2, p4);
-  const double p6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+  const double p6 = fma(r, d_expc[14], d_expc[13]);
   const double s = fma(fma(p6, r4, q2), r8, fma(q1, r4, q0));
   const int k = (int)kf;
   // 2^k * s by exponent arithmetic (s in [0.7, 1.5], k in [-1010, 1010])
