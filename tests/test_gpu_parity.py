@@ -114,7 +114,8 @@ def test_device_rad_ini_matches_oracle_tables():
     c.close()
 
 
-@pytest.mark.parametrize("cfg,n,nsrc,iso,sub", [(1, 24, 1, False, 10), (2, 20, 3, True, 20), (3, 24, 6, False, 5), (1, 17, 1, False, 4)])
+@pytest.mark.parametrize("cfg,n,nsrc,iso,sub", [(1, 24, 1, False, 10), (2, 20, 3, True, 20), (3, 24, 6, False, 5), (1, 17, 1, False, 4),
+                                                 (3, 64, 8, False, 10)])  # the 64^3 analogue of BASELINE configs[2]: big shells, BB+QPL
 def test_pass_all_sources(cfg, n, nsrc, iso, sub):
     p = synth.make_problem(cfg, n=n, num_src=nsrc, isothermal=iso)
     p["subboxsize"] = sub

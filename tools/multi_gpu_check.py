@@ -109,19 +109,26 @@ def main():
     for a, b, c1 in zip(h_split, h_repl, h_one):
         ok &= a[:3] == b[:3] == c1[:3]
         ok &= abs(a[3] - c1[3]) <= 1e-10 * abs(c1[3]) + 1e-300 and abs(a[4] - c1[4]) <= 1e-9
-    tol_sr = 0.0 if world == 2 else 1e-12
-    e_sr = max(relerr(x, y) for x, y in zip(s_split, s_repl))
-    ok &= e_sr <= tol_sr
-    # against one rank: fractions 1e-8 rel + 2e-10 abs (tests/common.py), T one float ulp, rates 1e-8
-    names = ["xh", "xhe", "T", "phih", "phihe", "phiheat", "xh_av", "xhe_av", "xh_int", "xhe_int"]
-    errs = {}
-    for n, x, y in zip(names, s_split, s_one):
+    # two ranks: a+b is the only sum, reduce-scatter and allreduce must agree bitwise.  More ranks: NCCL may add in a
+    # different order (1e-16 on the rate grids), which doric's cancellation noise turns into ~1e-11 absolute on the
+    # fractions (tests/common.py) -- compared with the parity tolerances, in units of them
+    def tol_err(n, x, y):
         if n in ("xh", "xhe", "xh_av", "xhe_av", "xh_int", "xhe_int"):
-            errs[n] = float(np.max(np.abs(x - y) / (1e-8 * np.abs(y) + 2e-10)))
-        elif n == "T":
-            errs[n] = float(np.max(np.abs(x.astype(np.float64) - y) / (1.3e-7 * np.abs(y) + 1e-30)))
-        else:
-            errs[n] = float(np.max(np.abs(x - y) / (1e-8 * np.abs(y) + 1e-300)))
+            return float(np.max(np.abs(x - y) / (1e-8 * np.abs(y) + 2e-10)))
+        if n == "T":
+            return float(np.max(np.abs(x.astype(np.float64) - y) / (1.3e-7 * np.abs(y) + 1e-30)))
+        return float(np.max(np.abs(x - y) / (1e-8 * np.abs(y) + 1e-300)))
+    names = ["xh", "xhe", "T", "phih", "phihe", "phiheat", "xh_av", "xhe_av", "xh_int", "xhe_int"]
+    if world == 2:
+        tol_sr = 0.0
+        e_sr = max(relerr(x, y) for x, y in zip(s_split, s_repl))
+        ok &= e_sr <= tol_sr
+    else:
+        tol_sr = 1.0
+        e_sr = max(tol_err(n, x, y) for n, x, y in zip(names, s_split, s_repl))
+        ok &= e_sr < tol_sr
+    # against one rank: fractions 1e-8 rel + 2e-10 abs (tests/common.py), T one float ulp, rates 1e-8
+    errs = {n: tol_err(n, x, y) for n, x, y in zip(names, s_split, s_one)}
     ok &= all(v < 1 for v in errs.values())
     # every rank holds the same full result
     mine = torch.tensor([float(np.sum(a.astype(np.float64))) for a in s_split], dtype=torch.float64, device="cuda")
