@@ -14,8 +14,10 @@ __device__ __forceinline__ double fast_rcp(double b) {
   double e = fma(-b, r, 1.0);
   e = fma(e, e, e);
   r = fma(r, e, r);
+#ifndef C2RAY_RCP_SHORT
   e = fma(-b, r, 1.0);
   r = fma(r, e, r);
+#endif
   return r;
 }
 
