@@ -1,24 +1,23 @@
 // c2ray_fastmath.cuh -- FP64 elementary functions without IEEE special-case scaffolding, for the argument ranges
 // that occur on the hot path (positive normal inputs to log, |x| < 700 for exp, normal divisors).  The general-purpose
 // CUDA log10/pow/exp and `/` cost 50-250 instructions each, most of it range checks and slow-path branches; these
-// cost 7-35 and are branch-free.  Relative errors are ~1-3e-16, i.e. the same order as the libm/libdevice
-// differences the parity tolerance (1e-8) already absorbs.
+// cost 5-35 and are branch-free.  Measured against libdevice (tools/check_fastmath.cu, 3e8 samples): fdiv equals a/b in
+// every sample, fast_log10 is within 1.8e-15 absolute on [1e-20, 1e4] (1.5e-13 of a table row), fast_log within 2.2e-16
+// relative, fast_exp within 4.4e-16 relative on |x| <= 700 -- the order of the libm/libdevice differences the parity
+// tolerance (1e-8) already absorbs.
 #pragma once
 
 namespace c2 {
 
-// 1/b : MUFU.RCP64H seed + cubic + Newton refinement, |rel err| ~ 2^-53 for normal b
+// 1/b : MUFU.RCP64H seed (measured relative error <= 2^-19.9) + one cubic step (e + e^2: error e^3 ~ 2^-60, then the
+// rounding of two FMAs).  Measured over 3e8 log-uniform b in [1e-30, 1e30]: max |1 - b r| = 1.00 x 2^-53, the same as with
+// a further Newton step (tools/check_fastmath.cu), which therefore is not taken.
 __device__ __forceinline__ double fast_rcp(double b) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
   double e = fma(-b, r, 1.0);
   e = fma(e, e, e);
-  r = fma(r, e, r);
-#ifndef C2RAY_RCP_SHORT
-  e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-#endif
-  return r;
+  return fma(r, e, r);
 }
 
 // a/b to ~1 ulp (not correctly rounded), no slow path
