@@ -1,15 +1,18 @@
 // c2ray_photo.cuh -- radiation_photoionrates.f90:108-277 photoion_rates for one cell, streamed over the frequency
-// bands (no 47-element work arrays), written for instruction count: the round-1 profile showed 22.8 k warp
-// instructions per source x cell update of which only a third were FP64 arithmetic -- the rest came from IEEE
-// division slow-path scaffolding, the general-purpose log10/pow, per-band divisions by the shell volume and scalar
-// gathers from 16 different table columns per band.
+// bands (no 47-element work arrays), written first for instruction count -- the first profile showed 22.8 k
+// instructions per source x cell update of which only a third were FP64 arithmetic, the rest IEEE division slow-path
+// scaffolding, the general-purpose log10/pow, per-band divisions by the shell volume and scalar gathers from 16
+// table columns per band -- and then for the footprint of its look-ups in the L1 and the constant cache.
 //   * 1/vol is applied once per cell, not per band (all rates are linear in it)
 //   * (log10(tau)-minlogtau)/dlogtau becomes one FMA with 1/dlogtau; the clamps of odpos move to the integer index
 //   * log10 is a branch-free atanh-series evaluation valid for the positive normal arguments that occur here
 //     (tau clamped to >= 1e-20), accurate to ~2e-16 relative, coefficients as constant-bank operands
-//   * reciprocals use MUFU.RCP64H + cubic/Newton refinement (error ~ 2^-54) without the IEEE slow path
-//   * the secondary-ionisation factors y1R, y2R (9 pow per cell in the reference, :557-565) depend on the cell only
-//     and are precomputed once per iteration by k_secion_factors
+//   * reciprocals use MUFU.RCP64H + one cubic step (|1 - b r| <= 2^-53 measured) without the IEEE slow path
+//   * the secondary-ionisation factors y1R, y2R (9 pow per cell in the reference, :557-565) depend on the cell only:
+//     they are computed once per iteration into the cell records (k_cell_records) and, being band independent factors
+//     of sums that are linear in the per-band heating, applied once per cell after the band loop (photoion_finish)
+//   * the band constants (3 cross sections, 12 f-factors) sit in one 128-byte record per band in constant memory
+//   * a source with several SEDs is traced SED by SED (rates are linear in the SEDs), see photoion_bands
 //   * the four tables of an SED are re-packed band-major into 32-byte rows, thick and thin values apart:
 //       thick(band, itau) = [photo_thick, heat_thick(HI,HeI,HeII)]   thin(band, itau) = [photo_thin, heat_thin(HI,HeI,HeII)]
 //     so one table position is two adjacent rows (64 contiguous bytes, 16-byte vector loads) instead of up to 8
