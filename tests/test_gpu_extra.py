@@ -234,3 +234,36 @@ def test_mrgrnk_on_the_device_is_bit_exact():
         assert np.array_equal(got, O.mrgrnk(x)), n
     assert c.mrgrnk(np.zeros(0, dtype=np.float32)).size == 0
     c.close()
+
+
+def test_edge_cases_no_sources_and_coincident_sources():
+    """NumSrc = 0 (evolve.F90:191 skips pass_all_sources: pure recombination / cooling, conv_criterion = 0 so the
+    iteration runs into its 500-iteration cap exactly as the reference's does) and two sources in one cell."""
+    p = synth.make_problem(2, n=16, num_src=2, isothermal=False)
+    p["NormFlux"] = p["NormFlux"] * 30.0
+    tables = oracle_setup(p)
+    # two sources at the same position: the rates add, the bookkeeping counts both
+    p2 = dict(p); p2["srcpos"] = np.array([p["srcpos"][0], p["srcpos"][0]], dtype=np.int32)
+    g = oracle_grid(p2)
+    so = g.evolve3d(p2["dt"])
+    c = c2ray_b200.from_problem(p2, tables=tables)
+    sg = c.evolve3D(0.0, p2["dt"], 0)
+    assert sg["niter"] == so["niter"] and sg["rt_updates"] == so["rt_updates"] and sg["sum_nbox_all"] == so["sum_nbox"]
+    assert frac_err(c.get_state()[0], g.get_state()[0]) < 1 and frac_err(c.get_state()[1], g.get_state()[1]) < 1
+    # no sources at all, from a partially ionized state
+    xh_av, xhe_av = partially_ionized_state(p)
+    p0 = dict(p); p0["srcpos"] = np.zeros((0, 3), dtype=np.int32); p0["NormFlux"] = np.zeros(0)
+    p0["xh"], p0["xhe"] = xh_av, xhe_av
+    g = oracle_grid(p0)
+    so = g.evolve3d(p0["dt"])
+    c.set_sources(p0["srcpos"], p0["NormFlux"])
+    c.set_state(p0["ndens"], xh_av, xhe_av, p0["temperature_grid"])
+    sg = c.evolve3D(0.0, p0["dt"], 0)
+    assert sg["niter"] == so["niter"] and sg["rt_updates"] == 0 and sg["conv_criterion"] == 0
+    assert list(sg["conv_hist"][:5]) == list(so["conv_hist"][:5])
+    if so["niter"] <= 500:   # converged: the state was copied back and must agree
+        assert frac_err(c.get_state()[0], g.get_state()[0]) < 1
+    for a, b in zip(c.get_work_state(), g.get_work_state()):
+        assert frac_err(a, b) < 1
+    assert not any(r.any() for r in c.get_rates())
+    c.close()
