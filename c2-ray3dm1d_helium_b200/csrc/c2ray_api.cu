@@ -387,7 +387,12 @@ int sweep_all(c2ray_ctx* c) {
   if (rc) return rc;
   int ngroups = 1;
   if (c->n_mine > 0) {
-    const int want = c->par.deterministic ? 1 : std::min(c->n_mine, c->par.max_slots > 0 ? c->par.max_slots : 1024);
+    int want = 1;
+    if (!c->par.deterministic) {  // a multiple of the group count, so that every group gets the same number of slots
+      const int gw = std::max(1, std::min(c->sweep_groups, c->n_mine));
+      want = std::min(c->n_mine, c->par.max_slots > 0 ? c->par.max_slots : 1024);
+      want = (want + gw - 1) / gw * gw;
+    }
     rc = alloc_sweep(c, want);
     if (rc) return rc;
     const SweepGeom g = c->geom;
@@ -397,8 +402,9 @@ int sweep_all(c2ray_ctx* c) {
     LAUNCH(c, k_cell_records, (unsigned)((c->N3 + 255) / 256), 256, c->ndens, c->xh_av, c->xhe_av, c->N3,
            c->par.isothermal ? 1 : 0, c->d_cellrec);
     GridPtrs G{c->d_cellrec, c->rates, c->N3, c->lls_type, c->coldensh_LLS, c->d_lls};
-    const int batch = c->par.deterministic ? 1 : c->slots_cap;
-    ngroups = c->par.deterministic ? 1 : std::max(1, std::min(c->sweep_groups, std::min(batch, c->n_mine)));
+    ngroups = c->par.deterministic ? 1 : std::max(1, std::min(c->sweep_groups, std::min(c->slots_cap, c->n_mine)));
+    const int region = c->par.deterministic ? 1 : c->slots_cap / ngroups;  // slots per stream group
+    const int batch = region * ngroups;                                     // sources in flight at a time
     static const int max_blocks = [] { const char* e = getenv("C2RAY_SWEEP_MAXBLOCKS"); return e ? std::max(1, atoi(e)) : 148 * 16; }();
     // A source whose PL and QPL fluxes are zero (or whose tables are absent) contributes through the black-body
     // tables only and takes the single-SED kernel, whatever other sources need: in a -DQUASARS run with QPL flux
@@ -435,13 +441,16 @@ int sweep_all(c2ray_ctx* c) {
       else if (first < c->n_single) { multi_sed = false; ns = std::min(batch, c->n_single - first); }
       else { multi_sed = true; ns = std::min(batch, c->n_mine - first); }
       struct Advance { int& f; int n; ~Advance() { f += n; } } advance{first, ns};
+      // Group q owns the fixed slot range [q*region, (q+1)*region) in every batch: batches follow each other on a
+      // group's own stream without any cross-stream wait, so a slot (its state, active-list entry and shell scratch)
+      // must never move to another group.  soff: where a group's sources start within the batch.
       const int per = (ns + ngroups - 1) / ngroups;
-      int goff[MAX_SWEEP_GROUPS], gns[MAX_SWEEP_GROUPS];
-      for (int q = 0; q < ngroups; q++) { goff[q] = std::min(q * per, ns); gns[q] = std::min(per, ns - goff[q]); }
+      int goff[MAX_SWEEP_GROUPS], soff[MAX_SWEEP_GROUPS], gns[MAX_SWEEP_GROUPS];
+      for (int q = 0; q < ngroups; q++) { goff[q] = q * region; soff[q] = std::min(q * per, ns); gns[q] = std::min(per, ns - soff[q]); }
       for (int q = 0; q < ngroups; q++)
         if (gns[q] > 0)
           LAUNCH_S(c, c->gstream[q], k_slots_init, (gns[q] + 127) / 128, 128, c->d_slots + goff[q], gns[q],
-                   c->d_srcids_run + first + goff[q], c->d_srcpos, c->d_nf, c->have_pl_flux ? c->d_nfpl : nullptr,
+                   c->d_srcids_run + first + soff[q], c->d_srcpos, c->d_nf, c->have_pl_flux ? c->d_nfpl : nullptr,
                    c->have_qpl_flux ? c->d_nfqpl : nullptr, c->d_gtot + q, c->d_active + goff[q]);
       const int reach3 = std::min(g.R[2], g.L[2]);
       int nact[MAX_SWEEP_GROUPS];

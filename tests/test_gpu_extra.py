@@ -267,3 +267,28 @@ def test_edge_cases_no_sources_and_coincident_sources():
         assert frac_err(a, b) < 1
     assert not any(r.any() for r in c.get_rates())
     c.close()
+
+
+def test_uneven_batches_keep_slots_within_their_stream_group():
+    """More sources than slots, odd counts, single- and multi-SED sources mixed: consecutive batches run on the groups'
+    own streams with no cross-stream wait, so a slot must never change groups between batches (a randomised run found a
+    source dropped when it did).  Repeated, because the failure was timing dependent."""
+    p = synth.make_problem(3, n=20, num_src=7)
+    p["NormFluxQPL"] = np.array([0.0, 3e3, 0.0, 2e3, 0.0, 0.0, 1e3])
+    p["subboxsize"] = 6
+    tables = oracle_setup(p)
+    xh_av, xhe_av = partially_ionized_state(p)
+    g = oracle_grid(p)
+    g.set_work_state(xh_av, xhe_av, xh_av, xhe_av)
+    g.set_rates_to_zero()
+    upd_o = g.pass_all_sources(order=1)[0]
+    ref = g.get_rates()
+    for slots in (3, 2, 5):
+        c = c2ray_b200.from_problem(p, tables=tables, max_slots=slots)
+        c.set_work_state(xh_av, xhe_av, xh_av, xhe_av)
+        for rep in range(6):
+            c.set_rates_to_zero()
+            assert c.pass_all_sources(1, p["dt"]) == upd_o, (slots, rep)
+            for a, b in zip(c.get_rates(), ref):
+                assert np.array_equal(a != 0, b != 0) and relerr(a, b, 1e-6 * np.abs(b).max() + 1e-300) < 1e-8, (slots, rep)
+        c.close()
