@@ -1,11 +1,14 @@
 """A second, independent restatement (plain numpy/Python, written from the Fortran, sharing no code with oracle/) of the
-two routines the sweep spends its time in, checked against the C++ oracle.  The reference ships no expected outputs
+routines the path spends its time in, checked against the C++ oracle.  The reference ships no expected outputs
 (SURVEY F3), so what pins the oracle is agreement between independent transcriptions plus the invariants in
 test_oracle_cpu.py.
 
   photoion_rates   code/radiation_photoionrates.f90:108-277 with set_tau_table_positions :282, read_table :310,
                    photo_lookuptable :331, heat_lookuptable :470, scale_int2/3 :787/:808
   cinterp          code/files_for_3D/column_density.f90:28-345, weightf :351-376
+  do_chemistry     code/files_for_3D/evolve_point.F90:444-646 (global branch) with thermal (thermal.f90:22-174), coolin
+                   (cooling_h.f90:40-71), cosmo_cool (cosmology.f90:207-234), prepare_doric_factors / coldens
+                   (doric.f90:317-372); doric itself through the oracle's single-call hook
 
 Only data is shared: the radiation tables (built by the oracle's rad_ini, itself checked in test_oracle_cpu.py) and the
 band constants parsed from oracle/band_data.h (literal arrays extracted from radiation_sizes.f90)."""
@@ -17,7 +20,7 @@ import numpy as np
 import pytest
 
 from c2ray_b200 import synth
-from common import O, oracle_setup
+from common import O, frac_err, oracle_setup
 
 F = lambda x: float(np.float32(x))  # a default-real literal of the reference
 NB1, NB2, NB3, NUMTAU = 1, 26, 20, 2000
@@ -228,3 +231,138 @@ def test_cinterp_against_numpy_restatement():
         ref = cinterp_np(q, src, mesh, cdh, cdhe[0], cdhe[1])
         worst = max(worst, float(np.max(np.abs(out - np.array(ref)) / np.abs(ref))))
     assert worst < 1e-14, worst   # the same IEEE operations in the same order: differences only from float() vs real()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# thermal (code/thermal.f90:22-174), coolin (cooling_h.f90:40-71), cosmo_cool (cosmology.f90:207-234) and the
+# do_chemistry iteration (files_for_3D/evolve_point.F90:444-646, global branch) in plain Python; doric itself is taken
+# from the oracle through its single-call hook (it has its own check against a 60-digit matrix exponential in
+# test_oracle_cpu.py), everything around it -- the order of the calls, the partial averaging, the convergence test, the
+# explicit thermal sub-cycling -- is restated here from the Fortran.
+# ------------------------------------------------------------------------------------------------------------------
+ABU_HE, ABU_C = F(0.074), F(7.1e-7)
+K_B, GAMMA1 = 1.381e-16, 5.0 / 3.0 - 1.0
+MINITEMP, REL_DENERGY = F(1.0), F(0.1)
+MFC, MFA = F(1.0e-2), F(1.0e-8)
+
+
+def electrondens_py(n, xh, xhe):  # tped.f90:75-84
+    return n * (xh[1] * (1.0 - ABU_HE) + ABU_C + ABU_HE * (xhe[1] + 2.0 * xhe[2]))
+
+
+def make_coolin():
+    logT, *cols = O.read_cooling_table()
+    lin = [10.0 ** np.asarray(c) for c in cols]                          # cooling_h.f90:163-169
+    mintemp, dtemp = logT[0], logT[1] - logT[0]
+
+    def coolin(n, ne, xh, xhe, T):
+        tpos = (np.log10(T) - mintemp) / dtemp + 1.0
+        it = min(801 - 1, max(1, int(tpos)))
+        d = tpos - float(it)
+        it1 = min(801, it + 1)
+        L = [c[it - 1] + (c[it1 - 1] - c[it - 1]) * d for c in lin]
+        return n * ne * ((xh[0] * L[0] + xh[1] * L[1]) * (1.0 - ABU_HE) + (xhe[0] * L[2] + xhe[1] * L[3] + xhe[2] * L[4]) * ABU_HE)
+    return coolin
+
+
+def thermal_py(dt, T, ne, n, ion, heat, coolin, cosmo):
+    """ion: dict h, he, h_av, he_av, h_old, he_old.  Returns (end_temper, avg_temper or None when untouched)."""
+    e_int = (n + electrondens_py(n, ion["h_old"], ion["he_old"])) * K_B * T / GAMMA1
+    cosmo_rate = 0.0
+    if cosmo is not None:
+        zred, H0, Om = cosmo
+        dzdt = H0 * (F(1.0) + zred) * np.sqrt(Om * (F(1.0) + zred) ** 3 + F(1.0) - Om)
+        cosmo_rate = e_int * F(2.0) / (F(1.0) + zred) * dzdt
+    if not T > MINITEMP:
+        return T, None
+    t_cum, avg, it, T0 = 0.0, 0.0, 0, T
+    ne_av = electrondens_py(n, ion["h_av"], ion["he_av"])
+    while True:
+        it += 1
+        cooling = coolin(n, ne, ion["h_av"], ion["he_av"], T) + cosmo_rate
+        rate = max(1e-50, abs(cooling - heat))
+        dt_ode = min(REL_DENERGY * (e_int / abs(rate)), dt - t_cum)
+        e_int = e_int + dt_ode * (heat - cooling)
+        avg = avg + F(0.5) * T * dt_ode
+        T = (e_int * GAMMA1) / (K_B * (n + ne_av))
+        avg = avg + F(0.5) * T * dt_ode
+        if T < MINITEMP:
+            e_int = (n + ne_av) * K_B * MINITEMP                                # :141, no /gamma1
+            T = MINITEMP
+        t_cum += dt_ode
+        if t_cum >= dt or abs(t_cum - dt) < F(1e-6) * dt or it > 10000:
+            break
+    avg = avg / dt if dt > 0.0 else T0
+    T_end = (e_int * GAMMA1) / (K_B * (n + electrondens_py(n, ion["h"], ion["he"])))
+    return T_end, avg
+
+
+def do_chemistry_py(dt, n, ion15, phi4, T_avg_in, T_old, coolin, cosmo, isothermal):
+    ion = np.array(ion15, dtype=np.float64)
+    sig = dict(H_heth=1.238e-18, H_heLya=9.907e-22, He_heLya=1.301e-20, He_he2=1.690780687052975e-18,
+               H_he2=1.230695924714239e-19, HeI=F(7.430e-18), HeII=F(1.589e-18))
+
+    def fracs():  # prepare_doric_factors(coldens(path=1,...)) doric.f90:317-372
+        NH = ion[0] * n * 1.0 * (1.0 - ABU_HE); NHe0 = ion[2] * n * 1.0 * ABU_HE; NHe1 = ion[3] * n * 1.0 * ABU_HE
+        a, b = NH * sig["H_heth"], NHe0 * sig["HeI"]
+        c, d = NH * sig["H_heLya"], NHe0 * sig["He_heLya"]
+        e, f, g = NH * sig["H_he2"], NHe0 * sig["He_he2"], NHe1 * sig["HeII"]
+        return [a / (a + b), c / (c + d), g / (g + f + e), f / (g + f + e)]
+
+    avg_temper, temper1 = T_avg_in, T_old
+    temper0 = temper1
+    nit = 0
+    while True:
+        nit += 1
+        temper2 = temper1
+        yh0, yhe0, yhe2 = ion[5], ion[7], ion[9]
+        de = electrondens_py(n, ion[5:7], ion[7:10])
+        ion = O.doric(dt, de, n, ion, phi4[:3], fracs(), avg_temper)
+        de = electrondens_py(n, ion[5:7], ion[7:10])
+        fr = fracs()
+        old = ion.copy()
+        ion = O.doric(dt, de, n, ion, phi4[:3], fr, avg_temper)
+        for q in (0, 1, 2, 3, 4, 5, 7, 8):                       # h(0:1) he(0:2) h_av(0) he_av(0:1); h_av(1), he_av(2) keep pass 2
+            ion[q] = (ion[q] + old[q]) / 2.0
+        de = electrondens_py(n, ion[5:7], ion[7:10])
+        temper1 = temper0
+        if not isothermal:
+            d = dict(h=ion[0:2], he=ion[2:5], h_av=ion[5:7], he_av=ion[7:10], h_old=ion[10:12], he_old=ion[12:15])
+            temper1, av = thermal_py(dt, temper1, de, n, d, phi4[3], coolin, cosmo)
+            if av is not None:
+                avg_temper = av
+        conv = ((abs((ion[5] - yh0) / ion[5]) < MFC or ion[5] < MFA) and (abs((ion[7] - yhe0) / ion[7]) < MFC or ion[7] < MFA) and
+                (abs((ion[9] - yhe2) / ion[9]) < MFC or ion[9] < MFA) and abs((temper1 - temper2) / temper1) < MFC)
+        if conv or nit > 400:
+            break
+    return ion, temper1, avg_temper, nit
+
+
+@pytest.mark.parametrize("iso", [False, True])
+def test_do_chemistry_and_thermal_against_python_restatement(iso):
+    p = synth.make_problem(2, n=8, isothermal=iso)
+    oracle_setup(p)
+    coolin = make_coolin()
+    cosmo = (p["zred"], p["H0"], p["Omega0"]) if p["cosmological"] else None
+    q = synth.make_chemistry_problem(96, seed=9, isothermal=iso)
+    n = 96
+    rng = np.random.default_rng(4)
+    x1 = 10.0 ** rng.uniform(-5, -0.01, n); a = 10.0 ** rng.uniform(-5, -0.3, n); b = a * 10.0 ** rng.uniform(-3, -0.2, n)
+    h = np.stack([1 - x1, x1], 1); he = np.stack([1 - a - b, a, b], 1)
+    ion15 = np.concatenate([h, he, h, he, h, he], axis=1)
+    ndens = np.ravel(q["ndens"])[:n]
+    phi4 = np.stack([np.ravel(q["phih"])[:n], np.ravel(q["phihe"][0])[:n], np.ravel(q["phihe"][1])[:n],
+                     np.ravel(q["phiheat"])[:n] if not iso else np.zeros(n)], 1)
+    T = np.float32(10.0 ** rng.uniform(3.5, 4.5, n)).astype(np.float64)
+    T3 = np.stack([T, T, T], 1)
+    ion_o, T_o, nit_o = O.chemistry_batch(q["dt"], ndens, ion15, phi4, T3)
+    assert nit_o.max() > 1
+    for c in range(n):
+        ion, t1, tav, nit = do_chemistry_py(q["dt"], ndens[c], ion15[c], phi4[c], p["temper_val"] if iso else T3[c, 1],
+                                            p["temper_val"] if iso else T3[c, 2], coolin, cosmo, iso)
+        assert nit == nit_o[c], (c, nit, nit_o[c])
+        # 1e-16 differences in the inputs handed to doric (summation order of the electron density) come back as
+        # ~1e-11 absolute from its cancellations: the parity tolerance of tests/common.py applies here too
+        assert frac_err(ion[:10], ion_o[c, :10]) < 1, (c, frac_err(ion[:10], ion_o[c, :10]))
+        if not iso:
+            assert abs(t1 / T_o[c, 0] - 1) < 1e-9 and abs(tav / T_o[c, 1] - 1) < 1e-9, (c, t1, tav, T_o[c])
