@@ -186,6 +186,10 @@ template <bool ISO, bool MULTI, int LANES>
 __global__ void __launch_bounds__(128, MULTI ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS)
 k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot, SweepGeom g,
               GridPtrs G, double* __restrict__ scratch, int r) {
+  // Programmatic dependent launch: within a sub-box level the next shell's launch is allowed to start filling SMs
+  // while this one drains (its threads decode their cell, test the box and fetch the cell record, then wait below
+  // before they touch the shell scratch).  Without the launch attribute both instructions are no-ops.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int nact = tot->nactive;
   const int ncell = shell_cells(r);
   const long long total = (long long)nact * ncell * LANES;
@@ -214,6 +218,9 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     const double2 rec0 = ld2(G.cellrec + p * (ISO ? CELLREC_ISO : CELLREC));      // xh_av(0) n, xhe_av(0) n
     const double2 rec1 = ld2(G.cellrec + p * (ISO ? CELLREC_ISO : CELLREC) + 2);  // xhe_av(1) n, -
 
+    // Everything above reads only what is constant within a sub-box level (slots, active list, cell records).  From
+    // here on the previous shell's column densities are read and the buffer it is still reading is overwritten.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     double cin_H, cin_He0, cin_He1, path, vol_ph;
     if (r == 0) {  // evolve_point.F90:140-150
       cin_H = 0.0; cin_He0 = 0.0; cin_He1 = 0.0;

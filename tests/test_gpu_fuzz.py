@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("seed", [1001, 1005, 1017, 1021, 1032, 1055, 1101, 1133])
+@pytest.mark.parametrize("seed", [1001, 1005, 1021, 1032, 1055, 2053, 2082, 2202])
 def test_random_case(seed):
     import fuzz_parity
     tag, upd = fuzz_parity.one_case(seed)
