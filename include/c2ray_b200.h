@@ -97,7 +97,7 @@ int c2ray_b200_destroy(c2ray_ctx* ctx);
 int c2ray_b200_set_params(c2ray_ctx* ctx, const c2ray_params* params);
 
 /* cooling_h.f90:76 setup_cool: logT[801] and 5 x log10(Lambda)[801] (H0, H1 caseB, He0, He1, He2) as read
- * from tables/*.tab; converted to linear (10**x) on upload as the reference does (:163-169). */
+ * from the tables/ directory (H0-cool.tab ...); converted to linear (10**x) on upload as the reference does (:163-169). */
 int c2ray_b200_set_cooling_tables(c2ray_ctx* ctx, const double* logT, const double* logLambda5x801);
 
 /* radiation_tables.f90:141 rad_ini executed on the device (table build kernel).  Alternatively the host's own
