@@ -121,3 +121,38 @@ def test_full_size_chemistry_idempotent_when_dark():
     xh_av, xhe_av, xh_i, xhe_i = c.get_work_state()
     assert xh_i[1].max() < 1e-4 and xhe_i[2].max() < 1e-10
     c.close()
+
+
+def test_full_size_config3_properties():
+    """BASELINE configs[2] at full size (256^3, 1000 sources, BB + QPL on the 50 brightest, subboxsize 10): properties that
+    need no oracle run -- repeatability of the integer bookkeeping, linearity of the rate grids in the source strengths
+    (the sub-box termination test is scale invariant), and the 2-rank source partition summing to the single-rank grids."""
+    p = synth.make_problem(3)
+    assert p["mesh"][0] == 256 and len(p["NormFlux"]) == 1000 and int((p["NormFluxQPL"] > 0).sum()) == 50
+    c = c2ray_b200.from_problem(p)
+    c.begin_step()
+    c.set_rates_to_zero()
+    upd = c.pass_all_sources(1, p["dt"])
+    r1 = c.get_rates()
+    assert upd > 1000 * 21 ** 3 and upd < 1000 * 256 ** 3    # every source traces at least its first sub-box
+    assert all(np.all(np.isfinite(a)) and a.min() >= 0 for a in r1) and r1[0].max() > 0 and r1[2].max() > 0
+    c.set_rates_to_zero()
+    assert c.pass_all_sources(1, p["dt"]) == upd
+    for a, b in zip(c.get_rates(), r1):
+        assert relerr(a, b, 1e-9 * np.abs(b).max() + 1e-300) < 1e-9      # atomics: summation order only
+    c.set_sources(p["srcpos"], 2.0 * p["NormFlux"], None, 2.0 * p["NormFluxQPL"])
+    c.set_rates_to_zero()
+    assert c.pass_all_sources(1, p["dt"]) == upd
+    for a, b in zip(c.get_rates(), r1):
+        assert relerr(a, 2.0 * b, 1e-9 * np.abs(b).max() + 1e-300) < 1e-9
+    c.set_sources(p["srcpos"], p["NormFlux"], None, p["NormFluxQPL"])
+    parts, upds = [], 0
+    for rank in (0, 1):
+        c.set_rank(rank, 2)
+        c.set_rates_to_zero()
+        upds += c.pass_all_sources(1, p["dt"])
+        parts.append(c.get_rates())
+    assert upds == upd
+    for k in range(3):
+        assert relerr(parts[0][k] + parts[1][k], r1[k], 1e-9 * np.abs(r1[k]).max() + 1e-300) < 1e-9
+    c.close()
