@@ -1423,6 +1423,16 @@ double orc_photon_loss() { return G.photon_loss_all[0]; }
 long orc_sum_nbox() { return G.sum_nbox_all; }
 
 // evolve.F90:435-501 global_pass (the loop :477-484); nit_out may be NULL; nthreads>1 only changes wall time
+// evolve0D_global over the cells [p0, p1) only (serial): what one rank does when the global pass is split over the ranks
+// (the reference runs the whole mesh on every rank, evolve.F90:477-484; cells are independent there).  Returns the number
+// of cells of the range that vote "not converged".
+int orc_global_pass_range(double dt, long p0, long p1) {
+  int conv_flag = 0;
+  long therm_total = 0;
+  for (long p = p0; p < p1; p++) evolve0D_global(dt, (size_t)p, conv_flag, &therm_total);
+  return conv_flag;
+}
+
 int orc_global_pass(double dt, int nthreads, int* nit_out) {
   const long N3 = (long)ncell();
   int conv_flag = 0;

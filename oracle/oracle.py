@@ -220,6 +220,9 @@ class Grid:
         cf = lib().orc_global_pass(C.c_double(dt), C.c_int(nthreads), None if nit is None else nit.ctypes.data_as(C.c_void_p))
         return (cf, nit) if want_nit else cf
 
+    def global_pass_range(self, dt, p0, p1):
+        return lib().orc_global_pass_range(C.c_double(dt), C.c_long(p0), C.c_long(p1))
+
     def evolve3d(self, dt, nthreads=1, order=0):
         stats = np.zeros(5, dtype=np.int64)
         hist = np.zeros(512, dtype=np.int32)
