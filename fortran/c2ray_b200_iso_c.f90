@@ -313,6 +313,9 @@ contains
     use material, only: ndens, xh, xhe, temperature_grid, isothermal
     use evolve_data, only: phih_grid, phihe_grid, phiheat, xh_av, xhe_av, xh_intermed, xhe_intermed, photon_loss_all
     use evolve_source, only: sum_nbox_all
+    use sizes, only: mesh
+    use photonstatistics, only: photon_loss, totrec, totcollisions, recomions, dh0, dhe0, dhe2, total_ion, &
+         report_photonstatistics, update_grandtotal_photonstatistics
     real(kind=dp), intent(in) :: time, dt
     integer, intent(in) :: restart
     type(c2ray_stats) :: st
@@ -333,6 +336,20 @@ contains
     photon_loss_all(:) = 0.0_dp
     photon_loss_all(1) = st%photon_loss_all
     sum_nbox_all = int(st%sum_nbox_all)
+    ! Photon statistics of the step (evolve.F90:225-227).  calculate_photon_statistics cannot be called on the host: its
+    ! total_rates reads the recombination coefficients the last do_chemistry call left in the cgsconstants module
+    ! (photonstatistics.f90:180-194), and that call now happened on the device.  The library evaluates the same sums
+    ! with the same coefficients; the module's public variables are filled from them and the host's own reporting runs.
+    photon_loss(:) = photon_loss_all(:)/(real(mesh(1))*real(mesh(2))*real(mesh(3)))   ! evolve.F90:457
+    totrec = st%totrec
+    totcollisions = st%totcollisions
+    recomions = st%recomions
+    dh0 = st%sums_before(1) - st%sums_after(1)      ! photonstatistics.f90:251-260 total_ionizations
+    dhe0 = st%sums_before(3) - st%sums_after(3)
+    dhe2 = st%sums_after(5) - st%sums_before(5)
+    total_ion = st%total_ion
+    call report_photonstatistics (dt)
+    call update_grandtotal_photonstatistics (dt)
     if (rank == 0) then
        write(logf,*) "Multiple sources convergence reached after ", st%niter, " iterations"
        write(logf,*) "Test 1 values: ", st%conv_flag, st%conv_criterion
