@@ -187,7 +187,7 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
     double phi_all, phi_out;
     double2 o0a = i0a, o1a = i1a;
     if (thick_p) {
-      o0a = ld2(ro); o1a = ld2(ro + PK_HALF);
+      o0a = ld2(ro); o1a = ld2(ro + PK_HALF);  // (skipping these loads when pout.ipos == pin.ipos: 7 % slower)
       phi_out = NFlux * lerp(o0a.x, o1a.x, pout.residual);
       phi_all = phi_in - phi_out;
     } else {
