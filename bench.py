@@ -33,11 +33,11 @@ UNIT = "updates/s"
 SRC_PER_GPU = 16
 MESH = 128
 BYTES_PER_UPDATE = 104  # 5 FP64 state reads + read-modify-write of 4 rate grids (thermal)
-# DRAM traffic of k_sweep_shell from the committed `ncu --set full` capture (profiles/r1_ncu_full_kernels_v3_128.csv,
+# DRAM traffic of k_sweep_shell from the committed `ncu --set full` capture (profiles/r1_ncu_full_kernels_final_v4_128.csv,
 # first launch = one stream group (8 sources) at shell radius 56: dram__bytes_read.sum + dram__bytes_write.sum =
-# 118.9 + 21.2 MB for 8 x 75,266 = 602,128 updates)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 140.1e6
-NCU_TRAFFIC_BYTES_PER_UPDATE = 232.7
+# 119.1 + 21.8 MB for 8 x 75,266 = 602,128 updates)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 140.9e6
+NCU_TRAFFIC_BYTES_PER_UPDATE = 234.0
 
 
 def workload(n_gpus, mesh):
