@@ -292,3 +292,39 @@ def test_uneven_batches_keep_slots_within_their_stream_group():
             for a, b in zip(c.get_rates(), ref):
                 assert np.array_equal(a != 0, b != 0) and relerr(a, b, 1e-6 * np.abs(b).max() + 1e-300) < 1e-8, (slots, rep)
         c.close()
+
+
+def test_sparse_cell_records_equal_the_full_build(monkeypatch):
+    """When the previous pass touched less than half the mesh, the per-cell sweep inputs are built only for the cells each
+    sub-box level is about to trace (k_cell_records_level).  Same rates as with the full build and as the oracle, also
+    after the state changed between passes."""
+    p = synth.make_problem(3, n=24, num_src=3)
+    p["max_subbox"] = 4
+    p["subboxsize"] = 2
+    tables = oracle_setup(p)
+    xh_a, xhe_a = partially_ionized_state(p, seed=3)
+    xh_b, xhe_b = partially_ionized_state(p, seed=4)
+    g = oracle_grid(p)
+    ref = []
+    for xh_av, xhe_av in ((xh_a, xhe_a), (xh_b, xhe_b)):
+        g.set_work_state(xh_av, xhe_av, xh_av, xhe_av); g.set_rates_to_zero()
+        upd_o = g.pass_all_sources(order=1)[0]
+        ref.append((upd_o, g.get_rates()))
+    assert ref[0][0] * 2 < 24 ** 3
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("C2RAY_SPARSE_RECORDS", mode)
+        c = c2ray_b200.from_problem(p, tables=tables)
+        out = []
+        for k, (xh_av, xhe_av) in enumerate(((xh_a, xhe_a), (xh_b, xhe_b), (xh_a, xhe_a))):   # passes 2 and 3 are sparse
+            c.set_work_state(xh_av, xhe_av, xh_av, xhe_av); c.set_rates_to_zero()
+            upd = c.pass_all_sources(k + 1, p["dt"])
+            assert upd == ref[k % 2][0]
+            out.append(c.get_rates())
+            for a, b in zip(out[-1], ref[k % 2][1]):
+                assert np.array_equal(a != 0, b != 0) and relerr(a, b, 1e-6 * np.abs(b).max() + 1e-300) < 1e-8, (mode, k)
+        res[mode] = out
+        c.close()
+    for x, y in zip(res["1"], res["0"]):
+        for a, b in zip(x, y):
+            assert relerr(a, b, 1e-300) < 1e-12
