@@ -31,9 +31,11 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                         \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
-    if (e_ != cudaSuccess)                                                                               \
+    if (e_ != cudaSuccess) {                                                                             \
+      cudaGetLastError(); /* reported here: do not leave it for a later, unrelated cudaGetLastError() */ \
       return fail(C2RAY_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
                                       std::to_string(__LINE__) + ")");                                   \
+    }                                                                                                    \
   } while (0)
 
 #define NC_(call)                                                                              \
@@ -801,6 +803,8 @@ extern "C" {
 
 const char* c2ray_b200_last_error(void) { return g_err.c_str(); }
 
+static int init_device_state(c2ray_ctx* c);
+
 int c2ray_b200_init(const c2ray_params* params, const int32_t mesh[3], int32_t device, c2ray_ctx** out) {
   if (!params || !mesh || !out) return fail(C2RAY_ERR_ARG, "null argument");
   if (mesh[0] < 2 || mesh[1] < 2 || mesh[2] < 2) return fail(C2RAY_ERR_ARG, "mesh must be >= 2 in every dimension");
@@ -819,6 +823,18 @@ int c2ray_b200_init(const c2ray_params* params, const int32_t mesh[3], int32_t d
   c->par = *params;
   for (int d = 0; d < 3; d++) c->mesh[d] = mesh[d];
   c->N3 = (size_t)mesh[0] * mesh[1] * mesh[2];
+  const int rc_alloc = init_device_state(c);
+  if (rc_alloc) {  // e.g. out of device memory half way: release what was allocated, keep the message
+    const std::string msg = g_err;
+    c2ray_b200_destroy(c);
+    return fail(rc_alloc, msg);
+  }
+  *out = c;
+  return C2RAY_OK;
+}
+
+static int init_device_state(c2ray_ctx* c) {
+  const int device = c->device;
   const size_t N3 = c->N3;
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -854,7 +870,6 @@ int c2ray_b200_init(const c2ray_params* params, const int32_t mesh[3], int32_t d
   int rc = upload_band_const(c);
   if (rc) return rc;
   c->run_dirty = true;
-  *out = c;
   return C2RAY_OK;
 }
 

@@ -328,3 +328,16 @@ def test_sparse_cell_records_equal_the_full_build(monkeypatch):
     for x, y in zip(res["1"], res["0"]):
         for a, b in zip(x, y):
             assert relerr(a, b, 1e-300) < 1e-12
+
+
+def test_failed_init_releases_the_device():
+    """Out of device memory half way through c2ray_b200_init: a clean error, nothing leaked, the next context works."""
+    import torch
+    free0 = torch.cuda.mem_get_info()[0]
+    with pytest.raises(capi.C2RayError, match="cudaMalloc"):
+        c2ray_b200.C2Ray([4096, 4096, 2048])          # 196 B x 3.4e10 cells
+    assert torch.cuda.mem_get_info()[0] > free0 - (64 << 20)
+    p = synth.make_problem(1, n=8)
+    c = c2ray_b200.from_problem(p)
+    assert c.evolve3D(0.0, p["dt"], 0)["niter"] >= 2
+    c.close()
