@@ -3,7 +3,7 @@
  * The reference (garrelt/C2-Ray3Dm1D_Helium) has no FFI: its seam is Fortran module procedures plus
  * `use`-associated module arrays.  Each entry point below names the reference routine it replaces
  * (file:line under code/), so a Fortran host keeps `evolve3D(time,dt,restart)` / `do_source(dt,ns1,niter)`
- * and forwards to these through iso_c_binding (see INTEGRATION.md and fortran/c2ray_b200_iso_c.f90).
+ * and forwards to these through iso_c_binding (see INTEGRATION.md and fortran/c2ray_b200_iso_c.F90).
  *
  * Conventions: plain pointers and sizes only.  Grid arrays are Fortran column-major A(i,j,k[,c]) --
  * i fastest, component slowest -- exactly as the reference's allocatables lie in memory; srcpos is

@@ -1,7 +1,7 @@
 /* A compiled-language host of libc2ray_b200.so: what the Fortran side does through iso_c_binding, written in C because
  * the image has no Fortran compiler.  It owns plain host arrays in the reference's memory layout
  * (column-major A(i,j,k,c), srcpos(3,NumSrc) 1-based, temperature_grid real(si)), and drives one time step exactly as
- * fortran/c2ray_b200_iso_c.f90 does: init -> cooling curves -> rad_ini -> sources -> geometry -> evolve3d_host -> rates.
+ * fortran/c2ray_b200_iso_c.F90 does: init -> cooling curves -> rad_ini -> sources -> geometry -> evolve3d_host -> rates.
  *
  *   evolve3d_driver <problem.bin> <result.bin>
  *
