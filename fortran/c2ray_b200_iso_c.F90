@@ -168,6 +168,21 @@ module c2ray_b200
 
 contains
 
+  !> Address of a host array that the reference declares without TARGET (temperature_grid, NormFluxQPL, ...): c_loc needs
+  !! a TARGET, and associating the actual argument with a TARGET dummy supplies one without touching the reference's
+  !! declarations.  The library only reads/writes through the pointer during the call it is passed to.
+  function loc_sp(a) result(p)
+    real(c_float), target, intent(in) :: a(*)
+    type(c_ptr) :: p
+    p = c_loc(a)
+  end function loc_sp
+
+  function loc_dp(a) result(p)
+    real(c_double), target, intent(in) :: a(*)
+    type(c_ptr) :: p
+    p = c_loc(a)
+  end function loc_dp
+
   !> Stop with the library's message: the reference has no error returns, it logs and stops (SURVEY 8b).
   subroutine check(rc, where)
     use file_admin, only: logf
@@ -296,7 +311,7 @@ contains
     type(c_ptr) :: pq
     pq = c_null_ptr
 #ifdef QUASARS
-    if (NumSrc > 0) pq = c_loc(NormFluxQPL(1))
+    if (NumSrc > 0) pq = loc_dp(NormFluxQPL)
 #endif
     ! NormFlux is dimensioned (0:NumSrc) in the reference: pass element 1 onwards
     call check(c2ray_b200_set_sources(ctx, int(NumSrc, c_int32_t), int(srcpos, c_int32_t), NormFlux(1:NumSrc), &
@@ -324,11 +339,11 @@ contains
     call check(c2ray_b200_set_geometry(ctx, dr, vol, zred), "set_geometry")   ! dr, vol, zred change every step
     ! material's set_clumping / set_LLS run once per redshift slice (C2Ray.F90): when type_of_clumping == 5 or use_LLS
     ! the host passes the fresh arrays here, e.g.
-    !   call check(c2ray_b200_set_clumping_grid(ctx, c_loc(clumping_grid)), "set_clumping_grid")
-    !   call check(c2ray_b200_set_LLS(ctx, int(type_of_LLS,c_int32_t), coldensh_LLS, c_loc(LLS_grid)), "set_LLS")
+    !   call check(c2ray_b200_set_clumping_grid(ctx, loc_sp(clumping_grid)), "set_clumping_grid")
+    !   call check(c2ray_b200_set_LLS(ctx, int(type_of_LLS,c_int32_t), coldensh_LLS, loc_sp(LLS_grid)), "set_LLS")
     ! (clumping_grid and LLS_grid are private to the material module: it needs two one-line accessor routines)
     pt = c_null_ptr
-    if (.not.isothermal) pt = c_loc(temperature_grid)
+    if (.not.isothermal) pt = loc_sp(temperature_grid)
     call check(c2ray_b200_evolve3d_host(ctx, time, dt, int(restart, c_int32_t), ndens, xh, xhe, pt, st), "evolve3d")
     ! what output.F90:354,364 and the final photon statistics (evolve.F90:225) read afterwards
     call check(c2ray_b200_get_rates(ctx, phih_grid, phihe_grid, phiheat), "get_rates")
