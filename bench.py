@@ -3,17 +3,18 @@
 
 Metric: source x cell RT updates/s (BASELINE.json), whole job, over full evolve3D time steps (ray-tracing sweeps of all
 sources + rate-grid reduction + global chemistry passes, iterated to convergence).
-Workload (N=1): BASELINE configs[1] -- Test-4 style 128^3 lognormal box, 16 black-body sources (T_eff=1e5 K,
-subboxsize=mesh), non-isothermal.  For N>1 every rank gets 16 sources of the same box (weak scaling); per iteration the
-rate grids are reduce-scattered, every rank runs the global pass on its N^3/npr cells and the fractions the next sweep
-reads are all-gathered (the reference: allreduce + replicated pass; same results, see tools/multi_gpu_check.py).
+Workload: BASELINE configs[2] -- 256^3 lognormal box, 1000 sources (BB 5e4 K + QPL on the 50 brightest), subboxsize 10,
+non-isothermal -- the largest source-sharded configuration that fits one GPU.  STRONG scaling: for N > 1 the same 1000
+sources are dealt over the ranks (balanced schedule); per iteration the rate grids are reduce-scattered, every rank runs
+the global pass on its N^3/npr cells and the fractions the next sweep reads are all-gathered.
 A step = one evolve3D(time,dt) from the same start state (device snapshot restored inside the timed region).
+`--workload config1` selects round 1's headline (BASELINE configs[1], 128^3, 16 sources per GPU, weak scaling).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config2|config1]
   torchrun ... bench.py --gpus N ...        (one rank per GPU)
 
---impl reference times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample of the same
-workload: one global iteration (RT pass over the 16 sources + global chemistry pass) per step.
+--impl reference times the CPU restatement of the reference (oracle/, all host threads of rank 0) on a bounded sample
+of the same workload, see CpuSample.
 """
 import argparse
 import json
@@ -30,34 +31,54 @@ sys.path.insert(0, ROOT)
 
 METRIC = "rt_source_cell_updates_per_s"
 UNIT = "updates/s"
-SRC_PER_GPU = 16
-MESH = 128
 BYTES_PER_UPDATE = 104  # 5 FP64 state reads + read-modify-write of 4 rate grids (thermal)
-# DRAM traffic of k_sweep_shell from the committed `ncu --set full` capture (profiles/r1_ncu_full_kernels_final_v4_128.csv,
-# first launch = one stream group (8 sources) at shell radius 56: dram__bytes_read.sum + dram__bytes_write.sum =
-# 119.1 + 21.8 MB for 8 x 75,266 = 602,128 updates)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 140.9e6
-NCU_TRAFFIC_BYTES_PER_UPDATE = 234.0
+
+# Workloads.  "config2" (default) is BASELINE configs[2] -- the largest configuration that is source-sharded AND fits one
+# GPU: 256^3 lognormal box, 1000 sources (black body 5e4 K; the 50 brightest also emit a hard quasar-like power law),
+# subboxsize 10, non-isothermal.  It is STRONG-scaled: the same 1000 sources are dealt over the N GPUs.
+# "config1" is BASELINE configs[1] (128^3 Test-4 style, 16 BB sources per GPU, weak scaling): round 1's headline, kept
+# for comparison (`--workload config1`).
+WORKLOADS = {
+    "config2": dict(config=3, mesh=256, sources=1000, scaling="strong", cpu_sample_sources=2,
+                    label="BASELINE configs[2]: 256^3 lognormal box (sigma=1.2, seed 256), 1000 sources at density peaks "
+                          "(BB T_eff=5e4 K; QPL index 1.8 on the 50 brightest), subboxsize=10, non-isothermal, dt=5 Myr"),
+    "config1": dict(config=2, mesh=128, sources=16, scaling="weak", cpu_sample_sources=16,
+                    label="BASELINE configs[1]: Test-4-style 128^3 lognormal box (sigma=1, seed 4), 16 BB sources per GPU "
+                          "T_eff=1e5 K, subboxsize=mesh, non-isothermal, dt=0.05 Myr"),
+}
+# Per-update figures of the dominant kernel taken from the committed ncu captures (profiles/, `tools/extract_ncu.py`):
+# FP64 flops (2 DFMA + DADD + DMUL thread instructions) and DRAM bytes per source x cell update.
+NCU_FIGURES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "sweep_kernel_figures.json")
 
 
-def workload(n_gpus, mesh):
+def workload(name, n_gpus, mesh=None):
     import c2ray_b200
-    p = c2ray_b200.synth.make_problem(2, n=mesh, num_src=SRC_PER_GPU * n_gpus, isothermal=False)
+    w = WORKLOADS[name]
+    n = mesh or w["mesh"]
+    if w["scaling"] == "strong":
+        return c2ray_b200.synth.make_problem(w["config"], n=n, num_src=w["sources"], isothermal=False)
+    p = c2ray_b200.synth.make_problem(w["config"], n=n, num_src=w["sources"] * n_gpus, isothermal=False)
     if n_gpus > 1:  # keep every source as bright as in the 16-source box
         p["NormFlux"] = p["NormFlux"] * n_gpus
     return p
 
 
-def config_dict(p, n_gpus):
-    return {"workload": f"BASELINE configs[1]: Test-4-style {p['mesh'][0]}^3 lognormal box (sigma=1, seed 4), "
-                        f"{len(p['NormFlux'])} BB sources T_eff=1e5 K, subboxsize=mesh, non-isothermal, dt=0.05 Myr, "
-                        "one full evolve3D time step per step",
-            "mesh": int(p["mesh"][0]), "sources": int(len(p["NormFlux"])), "sources_per_gpu": SRC_PER_GPU,
-            "parallelism": ("one GPU" if n_gpus == 1 else
-                            f"sources round-robin over {n_gpus} GPUs (do_grid_static); per iteration one reduce-scatter of the "
-                            "rate grids, the global pass on N^3/npr cells per rank, one all-gather of the fractions the next "
-                            "sweep reads"),
-            "l2_policy": "per-step working set (state + rate grids + snapshot, >400 MB) exceeds the 126 MB L2"}
+def config_dict(name, p, n_gpus):
+    w = WORKLOADS[name]
+    ns = int(len(p["NormFlux"]))
+    if n_gpus == 1:
+        par = "one GPU"
+    elif w["scaling"] == "strong":
+        par = (f"the {ns} sources dealt over {n_gpus} GPUs (balanced by the previous pass's cost, master_slave.F90 analogue); per "
+               "iteration one reduce-scatter of the rate grids, the global pass on N^3/npr cells per rank, one all-gather of the "
+               "fractions the next sweep reads")
+    else:
+        par = (f"sources round-robin over {n_gpus} GPUs (do_grid_static); per iteration one reduce-scatter of the rate grids, the "
+               "global pass on N^3/npr cells per rank, one all-gather of the fractions the next sweep reads")
+    return {"workload": w["label"] + "; one full evolve3D time step per step", "name": name, "mesh": int(p["mesh"][0]),
+            "sources": ns, "scaling": w["scaling"], "parallelism": par,
+            "l2_policy": "per-step working set (state + rate grids + cell records + snapshot, several hundred MB to GB) exceeds "
+                         "the 126 MB L2"}
 
 
 class ClockSampler:
@@ -116,20 +137,51 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_iteration(p, nthreads, sources=None):
-    """One global iteration of the oracle (reference restatement) on host threads: RT pass + global pass.
-    Returns (rt_updates, seconds_rt, seconds_chem)."""
-    from oracle import oracle as O
-    O.rad_ini(p["T_eff"], p["S_star"], qpl=p.get("qpl"), isothermal=p["isothermal"])
-    O.set_params(p["isothermal"], p["temper_val"], p["clumping"], p["zred"], p["H0"], p["Omega0"], p["cosmological"],
-                 p["subboxsize"], p["max_subbox"])
-    g = O.Grid(p["mesh"], p["dr"], p["vol"])
-    g.set_state(p["ndens"], p["xh"], p["xhe"], p["temperature_grid"])
-    ns = len(p["NormFlux"]) if sources is None else sources
-    g.set_sources(p["srcpos"][:ns], p["NormFlux"][:ns], None, None if p.get("NormFluxQPL") is None else p["NormFluxQPL"][:ns])
-    g.set_work_state(p["xh"], p["xhe"], p["xh"], p["xhe"])
-    g.set_rates_to_zero()
-    return g, ns
+class CpuSample:
+    """The bounded CPU sample of a workload, on the oracle (the C++ restatement of the reference; the Fortran itself
+    cannot be built in this image).  Set-up, untimed: global iteration 1 of the time step over ALL sources from the
+    neutral start state (RT pass + global chemistry pass), so that the sample sees the ionized bubbles the GPU arm sees
+    for 24 of its 25 iterations.  One timed sample: the RT pass of iteration 2 over the workload's `k` brightest sources
+    (for configs[2] these are BB+QPL sources that trace the whole box -- the 50 such sources are 99 % of the GPU arm's
+    updates) with every host thread busy (sources over threads, idle threads inside a source's shells), plus the
+    k/NumSrc share of one global chemistry pass."""
+
+    def __init__(self, name, p, nthreads):
+        from oracle import oracle as O
+        self.O, self.p, self.nthreads = O, p, nthreads
+        w = WORKLOADS[name]
+        self.ns_all = len(p["NormFlux"])
+        self.k = min(w["cpu_sample_sources"], self.ns_all)
+        O.rad_ini(p["T_eff"], p["S_star"], qpl=p.get("qpl"), isothermal=p["isothermal"])
+        O.set_params(p["isothermal"], p["temper_val"], p["clumping"], p["zred"], p["H0"], p["Omega0"], p["cosmological"],
+                     p["subboxsize"], p["max_subbox"])
+        g = self.g = O.Grid(p["mesh"], p["dr"], p["vol"])
+        g.set_state(p["ndens"], p["xh"], p["xhe"], p["temperature_grid"])
+        q = p.get("NormFluxQPL")
+        g.set_sources(p["srcpos"], p["NormFlux"], None, q)
+        g.set_work_state(p["xh"], p["xhe"], p["xh"], p["xhe"])
+        g.set_rates_to_zero()
+        t0 = time.perf_counter()
+        g.pass_all_sources(nthreads=nthreads, order=2)
+        t1 = time.perf_counter()
+        g.global_pass(p["dt"], nthreads=nthreads)
+        self.t_chem = time.perf_counter() - t1          # one global chemistry pass over the whole mesh
+        self.t_setup = time.perf_counter() - t0
+        g.set_sources(p["srcpos"][:self.k], p["NormFlux"][:self.k], None, None if q is None else q[:self.k])
+
+    def run(self):
+        """-> (updates, seconds) of one sample."""
+        self.g.set_rates_to_zero()
+        t0 = time.perf_counter()
+        upd, _, _, _ = self.g.pass_all_sources(nthreads=self.nthreads, order=2)
+        t_rt = time.perf_counter() - t0
+        return upd, t_rt + self.t_chem * self.k / self.ns_all, t_rt
+
+    def describe(self):
+        n = int(self.p["mesh"][0])
+        return (f"RT pass of global iteration 2 over the {self.k} brightest of the {self.ns_all} sources + {self.k}/{self.ns_all} of one "
+                f"global chemistry pass ({self.t_chem:.2f} s for the {n}^3 mesh), after an untimed iteration 1 over all sources "
+                f"({self.t_setup:.1f} s); C++ restatement of the reference (oracle/, g++ -O2 -fopenmp), {self.nthreads} threads")
 
 
 def run_reference(args):
@@ -137,30 +189,22 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
+    nthreads = O.set_num_threads()   # all CPUs of this process (torchrun exports OMP_NUM_THREADS=1 to its children)
     n_gpus = int(os.environ.get("WORLD_SIZE", args.gpus))
-    p = workload(n_gpus, args.mesh)   # the same config as the GPU arm at this N
-    nthreads = O.num_threads()
-    # bounded sample: at most 32 sources per step (each source costs ~2.1 M updates ~ 0.25 core-seconds x 8)
-    g, ns = cpu_reference_iteration(p, nthreads, sources=min(len(p["NormFlux"]), 32))
+    p = workload(args.workload, n_gpus, args.mesh)   # the same config as the GPU arm at this N
+    cs = CpuSample(args.workload, p, nthreads)
     times, updates = [], 0
     for step in range(args.warmup + args.steps):
-        g.set_work_state(p["xh"], p["xhe"], p["xh"], p["xhe"])
-        g.set_state(p["ndens"], p["xh"], p["xhe"], p["temperature_grid"])
-        g.set_rates_to_zero()
-        t0 = time.perf_counter()
-        upd, _, _, _ = g.pass_all_sources(nthreads=nthreads, order=0)
-        g.global_pass(p["dt"], nthreads=nthreads)
-        dt = time.perf_counter() - t0
+        upd, dt, _ = cs.run()
         if step >= args.warmup:
             times.append(dt); updates += upd
     total = sum(times)
     value = updates / total
-    sample = (f"per step: one global iteration (RT pass over {ns} of {len(p['NormFlux'])} sources + global chemistry pass) of the {args.mesh}^3 "
-              f"workload from the neutral start state, C++ restatement of the reference, g++ -O2 -fopenmp")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(p, n_gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+            "scaling": WORKLOADS[args.workload]["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args.workload, p, n_gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": "per step: " + cs.describe()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -181,12 +225,15 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    p = workload(n_gpus, args.mesh)
+    w = WORKLOADS[args.workload]
+    p = workload(args.workload, n_gpus, args.mesh)
     c = c2ray_b200.from_problem(p, device=local)
     if world > 1:
         uid = [c2ray_b200.C2Ray.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         c.comm_init(uid[0], rank, world)
+        if w["scaling"] == "strong":
+            c.set_source_schedule(1)   # balanced deal from the previous pass's cost records
     c.snapshot_state()
     N3 = c.N3
 
@@ -204,7 +251,7 @@ def run_b200(args):
     barrier()
     if rank == 0:
         sampler.start()
-    l0 = c.launch_count()
+    l0, sl0 = c.launch_count(), c.sweep_launch_count()
     c.timer_start()
     for step in range(args.steps):
         c.restore_state()
@@ -213,10 +260,12 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = c.launch_count() - l0
+    sweep_launches = c.sweep_launch_count() - sl0
     upd_local = sum(s["rt_updates"] for s in stats)
     ms_sweep = sum(s["ms_sweep"] for s in stats)
     ms_chem = sum(s["ms_chem"] for s in stats)
     ms_ar = sum(s["ms_allreduce"] for s in stats)
+    niter_total = sum(s["niter"] for s in stats)
 
     # ---- end-to-end arm: host buffers through the Fortran-facing entry point ------------------------------------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -240,54 +289,65 @@ def run_b200(args):
         t = torch.tensor([ms, t_e2e, ms_sweep, ms_chem, ms_ar], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, t_e2e, ms_sweep_max, ms_chem_max, ms_ar_max = t.tolist()
-        u = torch.tensor([upd_local, upd_e2e, launches], dtype=torch.float64, device="cuda")
+        u = torch.tensor([upd_local, upd_e2e, launches, ms_sweep], dtype=torch.float64, device="cuda")
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
-        upd_total, upd_e2e_total, launches_total = u.tolist()
+        upd_total, upd_e2e_total, launches_total, ms_sweep_sum = u.tolist()
     else:
         upd_total, upd_e2e_total, launches_total = upd_local, upd_e2e, launches
-        ms_sweep_max, ms_chem_max, ms_ar_max = ms_sweep, ms_chem, ms_ar
+        ms_sweep_max, ms_chem_max, ms_ar_max, ms_sweep_sum = ms_sweep, ms_chem, ms_ar, ms_sweep
 
     if rank == 0:
         value = upd_total / (ms * 1e-3)
         peak, peak_src = measured_peaks()
-        # dominant kernel: k_sweep_shell.  achieved = algorithmic bytes (104 B x updates of this rank) / its device time.
-        sweep_gbs = BYTES_PER_UPDATE * upd_local / (ms_sweep * 1e-3) / 1e9
-        fp64 = c.measure_fp64()
-        roofline = {"kernel": "k_sweep_shell", "bound": "hbm", "achieved": sweep_gbs, "peak": peak, "unit": "GB/s",
-                    "frac": sweep_gbs / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_note": "ncu capture of one r=56 launch (602 k updates): "
-                    f"{NCU_TRAFFIC_BYTES_PER_UPDATE:.0f} B/update measured vs {BYTES_PER_UPDATE} B algorithmic (64-byte DRAM granules on the strided "
-                    "x-faces of a shell for the 80-byte cell records and the rate-grid atomics; shell scratch)", "peak_source": peak_src,
-                    "launches": int(launches), "avg_launch_ms": ms_sweep / max(1, sum(s["niter"] for s in stats)) ,
-                    "note": "the sweep is FP64/LSU bound, not HBM bound (SURVEY F6): see fp64 fields",
-                    "updates_per_s_kernel": upd_local / (ms_sweep * 1e-3), "fp64_peak_tflops_measured": fp64,
+        fig = {}
+        if os.path.exists(NCU_FIGURES):
+            fig = json.load(open(NCU_FIGURES)).get(args.workload, {})
+        # dominant kernel: the ray-tracing sweep.  Its rate on this rank = this rank's updates / its event-timed duration.
+        upd_per_s_kernel = upd_local / (ms_sweep * 1e-3)
+        sweep_gbs = BYTES_PER_UPDATE * upd_per_s_kernel / 1e9
+        fp64_peak = c.measure_fp64()
+        flops_per_update = fig.get("fp64_flops_per_update")
+        fp64_tflops = flops_per_update * upd_per_s_kernel / 1e12 if flops_per_update else None
+        traffic_per_update = fig.get("dram_bytes_per_update")
+        launch_updates = upd_local / max(1, sweep_launches)
+        # The kernel is bound by the FP64 pipe, not by HBM (~6 kFLOP of FP64 per 104 algorithmic bytes), so the
+        # roofline that binds is FP64: achieved = FP64 flops per update (ncu instruction counts of the committed capture) x
+        # this run's updates/s of the kernel; peak = the DFMA rate measured on this GPU in this run.  The HBM view the
+        # contract asks for (104 B x updates/s over the measured copy bandwidth) is carried next to it.
+        roofline = {"kernel": fig.get("kernel", "k_sweep_shell"), "bound": "fp64",
+                    "achieved": fp64_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": (fp64_tflops / fp64_peak) if fp64_tflops else None,
+                    "fp64_achieved_tflops": fp64_tflops, "fp64_peak_tflops_measured": fp64_peak,
+                    "fp64_frac": (fp64_tflops / fp64_peak) if fp64_tflops else None,
+                    "fp64_flops_per_update": flops_per_update, "figures_source": fig.get("source"),
+                    "hbm_achieved_gbs": sweep_gbs, "hbm_peak_gbs": peak, "hbm_frac": sweep_gbs / peak, "hbm_peak_source": peak_src,
+                    "hbm_algorithmic_bytes_per_update": BYTES_PER_UPDATE,
+                    "traffic": (traffic_per_update * launch_updates) if traffic_per_update else None,
+                    "traffic_bytes_per_update": traffic_per_update,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per update of the committed `ncu --set full` capture "
+                                    "x this run's mean updates per launch (not re-measured in this run)",
+                    "sweep_launches": int(sweep_launches), "avg_launch_ms": ms_sweep / max(1, sweep_launches),
+                    "avg_launch_updates": launch_updates, "ms_per_rt_pass": ms_sweep / max(1, niter_total),
+                    "updates_per_s_kernel": upd_per_s_kernel,
                     "chem_cells_per_s": sum(s["chem_cells"] for s in stats) / (ms_chem * 1e-3),
                     "chem_hbm_frac": 224 * sum(s["chem_cells"] for s in stats) / (ms_chem * 1e-3) / 1e9 / peak,
-                    "ms_sweep": ms_sweep, "ms_chem": ms_chem, "ms_allreduce": ms_ar}
+                    "ms_sweep": ms_sweep, "ms_chem": ms_chem, "ms_allreduce": ms_ar,
+                    "ms_sweep_max_over_ranks": ms_sweep_max, "ms_sweep_mean_over_ranks": ms_sweep_sum / world,
+                    "ms_collectives_max_over_ranks": ms_ar_max}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": config_dict(p, n_gpus), "clocks": clocks,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, p, n_gpus), "clocks": clocks,
                 "e2e": {"value": upd_e2e_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "s_per_timestep": t_e2e / e2e_steps},
                 "gpu_launches": int(launches_total), "roofline": roofline,
                 "niter_per_step": stats[0]["niter"], "s_per_timestep": ms * 1e-3 / args.steps}
         if n_gpus == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
-            nthreads = O.num_threads()
-            ns = min(len(p["NormFlux"]), max(1, nthreads))
-            g, ns = cpu_reference_iteration(p, nthreads, sources=ns)
-            t0 = time.perf_counter()
-            upd, _, _, _ = g.pass_all_sources(nthreads=nthreads, order=0)
-            t_rt = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            g.global_pass(p["dt"], nthreads=nthreads)
-            t_ch = time.perf_counter() - t0
-            # scale the chemistry share to the full source count so the ratio of sweeps to chemistry matches the workload
-            frac = ns / len(p["NormFlux"])
-            line["cpu_baseline"] = {"value": upd / (t_rt + t_ch * frac), "unit": UNIT, "cores": nthreads, "kind": "port",
-                                    "sample": f"RT pass over {ns} of the {len(p['NormFlux'])} sources ({upd} updates, {t_rt:.1f} s) + "
-                                              f"{frac:.2f} x one global chemistry pass ({t_ch:.1f} s) of the same {args.mesh}^3 workload; "
-                                              "C++ restatement of the reference (oracle/), OpenMP over sources",
-                                    "rt_updates_per_s": upd / t_rt, "chem_cells_per_s": N3 / t_ch}
+            nthreads = O.set_num_threads()
+            cs = CpuSample(args.workload, p, nthreads)
+            upd, dt, t_rt = cs.run()
+            line["cpu_baseline"] = {"value": upd / dt, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": cs.describe(),
+                                    "rt_updates_per_s": upd / t_rt, "chem_cells_per_s": N3 / cs.t_chem}
         print(json.dumps(line))
     c.close()
     if world > 1:
@@ -300,7 +360,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mesh", type=int, default=MESH)
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mesh", type=int, default=None, help="override the workload's mesh (smoke runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -20,7 +20,7 @@ EXPORTS = [
     "c2ray_b200_global_pass", "c2ray_b200_end_step", "c2ray_b200_state_sums", "c2ray_b200_photoion_rates_batch",
     "c2ray_b200_chemistry_batch", "c2ray_b200_rec_colion_batch", "c2ray_b200_cinterp_batch",
     "c2ray_b200_comm_unique_id", "c2ray_b200_comm_init", "c2ray_b200_set_rank", "c2ray_b200_rates_device_buffer",
-    "c2ray_b200_bench_global_pass", "c2ray_b200_launch_count", "c2ray_b200_measure_fp64", "c2ray_b200_stream",
+    "c2ray_b200_bench_global_pass", "c2ray_b200_launch_count", "c2ray_b200_sweep_launch_count", "c2ray_b200_measure_fp64", "c2ray_b200_stream",
     "c2ray_b200_timer_start", "c2ray_b200_timer_stop",
     "c2ray_b200_set_dump", "c2ray_b200_write_iteration_dump", "c2ray_b200_read_iteration_dump",
     "c2ray_b200_write_stream2", "c2ray_b200_write_stream3", "c2ray_b200_fortran_records_write",
@@ -76,6 +76,9 @@ def load():
     L.c2ray_b200_last_error.restype = C.c_char_p
     L.c2ray_b200_launch_count.restype = C.c_int64
     L.c2ray_b200_launch_count.argtypes = [C.c_void_p]
+    if hasattr(L, "c2ray_b200_sweep_launch_count"):
+        L.c2ray_b200_sweep_launch_count.restype = C.c_int64
+        L.c2ray_b200_sweep_launch_count.argtypes = [C.c_void_p]
     for name in EXPORTS:
         try:
             fn = getattr(L, name)
@@ -83,7 +86,7 @@ def load():
             if "C2RAY_B200_LIB" in os.environ:  # an older tuning build loaded for an A/B timing
                 continue
             raise
-        if name not in ("c2ray_b200_last_error", "c2ray_b200_launch_count"):
+        if name not in ("c2ray_b200_last_error", "c2ray_b200_launch_count", "c2ray_b200_sweep_launch_count"):
             fn.restype = C.c_int
     _lib = L
     return L

@@ -142,6 +142,8 @@ struct c2ray_ctx {
   double* d_sums = nullptr;
   double* d_cellrec = nullptr;  // per-cell sweep inputs, rebuilt every iteration (k_cell_records)
   unsigned long long* d_next_cell = nullptr;
+  int n_sm = 148;          // multiprocessors of this context's device
+  int chemq_per_sm = 0;    // resident CTAs per SM of k_global_pass_q (queried once per context)
   int chem_mode = -1;      // -1 auto, 0 one cell per thread, 1 queue-driven (env C2RAY_CHEM_QUEUE overrides)
   double last_nsub_per_cell = 0.0;  // thermal sub-steps per cell of the previous global pass
   int* d_nit = nullptr;
@@ -169,6 +171,7 @@ struct c2ray_ctx {
   void* h_stage = nullptr;        // pinned staging buffer for device <-> file traffic
   // bookkeeping
   int64_t launches = 0;
+  int64_t sweep_launches = 0;  // k_sweep_* launches only (bench.py: mean duration of the dominant kernel)
   bool run_dirty = true;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_timer[2] = {nullptr, nullptr};
@@ -216,7 +219,7 @@ int bind(c2ray_ctx* c) {
 }
 
 int upload_band_const(c2ray_ctx* c) {
-  static BandRec bc[NumFreqBnd];
+  BandRec bc[NumFreqBnd];
   memset(bc, 0, sizeof(bc));
   bc[0].sigma_HI = sigma_HI_at_ion_freq;  // radiation_sizes.f90:381-383
   for (int i = 0; i < 26; i++) {
@@ -523,7 +526,7 @@ int sweep_all(c2ray_ctx* c) {
     CK(launch_overlapped(k_sweep_shell<ISO, MULTI, LANES>, (unsigned)blocks, 128u, c->gstream[q], pdl, c->d_slots + goff[q],  \
                          (const int*)(c->d_active + goff[q]), c->d_gtot + q, g, G,                                            \
                          c->d_scratch + (size_t)goff[q] * slot_stride, r));                                                   \
-    c->launches++;                                                                                                            \
+    c->launches++; c->sweep_launches++;                                                                                        \
   } while (0)
 #define SWEEP2(ISO, MULTI) do { if (split) SWEEP(ISO, MULTI, SPLIT_LANES); else SWEEP(ISO, MULTI, 1); } while (0)
             if (multi_sed) { if (c->par.isothermal) SWEEP2(true, true); else SWEEP2(false, true); }
@@ -611,7 +614,7 @@ int write_iteration_dump_file(c2ray_ctx* c, const std::string& path, int niter) 
   const size_t N3 = c->N3;
   c2io::RecordWriter w;
   if (!w.open(path)) return fail(C2RAY_ERR_STATE, "cannot open " + path + " for writing");
-  int rc;
+  int rc = 0;
   const int32_t ni = niter;
   if (!w.record(&ni, 4)) return fail(C2RAY_ERR_STATE, "short write");
   if (!w.begin(NumFreqBnd * 8) || (rc = put_device(c, w, c->rates + 4 * N3, NumFreqBnd * 8))) return rc ? rc : fail(C2RAY_ERR_STATE, "short write");
@@ -751,13 +754,11 @@ int global_pass_launch(c2ray_ctx* c, double dt, int* d_nit, size_t p_begin = 0, 
   if (use_queue) {
     // queue-driven: a persistent grid of lanes drawing cells from a counter (k_global_pass_q)
     CK(cudaMemsetAsync(c->d_next_cell, 0, sizeof(unsigned long long), c->stream));
-    static int per_sm = 0, n_sm = 0;
-    if (!per_sm) {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_global_pass_q, 128, 0));
-      CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
-      per_sm = std::max(per_sm, 1);
+    if (!c->chemq_per_sm) {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->chemq_per_sm, k_global_pass_q, 128, 0));
+      c->chemq_per_sm = std::max(c->chemq_per_sm, 1);
     }
-    const unsigned blocks = (unsigned)std::min<size_t>((ncell + 127) / 128, (size_t)n_sm * per_sm);
+    const unsigned blocks = (unsigned)std::min<size_t>((ncell + 127) / 128, (size_t)c->n_sm * c->chemq_per_sm);
     LAUNCH(c, k_global_pass_q, blocks, 128, P, dt, c->d_chem, d_nit, c->d_next_cell, p_begin, p_end);
   } else {
     const unsigned blocks = (unsigned)((ncell + 127) / 128);
@@ -837,6 +838,7 @@ static int init_device_state(c2ray_ctx* c) {
   const int device = c->device;
   const size_t N3 = c->N3;
   CK(cudaSetDevice(device));
+  CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
   for (auto& ev : c->ev_timer) CK(cudaEventCreate(&ev));
@@ -953,6 +955,10 @@ int c2ray_b200_upload_tables(c2ray_ctx* c, int32_t s, const c2ray_sed_tables* t)
     return pack_tables(c, s);
   }
   if (!t->photo_thin) return fail(C2RAY_ERR_ARG, "photo_thin missing");
+  // the band limits index the packed tables and the band records on the device (radiation_tables.f90:194-247)
+  if (t->freqbnd_lower < 1 || t->freqbnd_upper > NumFreqBnd || t->freqbnd_lower > t->freqbnd_upper + 1)
+    return fail(C2RAY_ERR_ARG, "FreqBnd limits must satisfy 1 <= lower, upper <= NumFreqBnd (47), lower <= upper + 1");
+  if (!std::isfinite(t->S_star) || t->S_star < 0.0) return fail(C2RAY_ERR_ARG, "S_star must be finite and non-negative");
   const bool heat = t->heat_thick && t->heat_thin;
   if (!heat && !c->par.isothermal) return fail(C2RAY_ERR_ARG, "heating tables required unless isothermal");
   int rc = ensure_tables(c, s, heat);
@@ -988,7 +994,8 @@ int c2ray_b200_download_table(c2ray_ctx* c, int32_t s, int32_t kind, double* out
 int c2ray_b200_rad_ini(c2ray_ctx* c, const c2ray_sed_params* sp) {
   if (!c || !sp) return fail(C2RAY_ERR_ARG, "null argument");
   CK(cudaSetDevice(c->device));
-  static TableBuild tb;
+  std::vector<TableBuild> tb_store(1);  // per call (the struct holds this context's device pointers)
+  TableBuild& tb = tb_store[0];
   memset(&tb, 0, sizeof(tb));
   double fmin[NumFreqBnd], fmax[NumFreqBnd], dfreq[NumFreqBnd];
   band_edges(fmin, fmax, dfreq);
@@ -1061,6 +1068,18 @@ int c2ray_b200_rad_ini(c2ray_ctx* c, const c2ray_sed_params* sp) {
 int c2ray_b200_set_sources(c2ray_ctx* c, int32_t NumSrc, const int32_t* srcpos, const double* nf, const double* nfpl,
                            const double* nfqpl) {
   if (!c || NumSrc < 0 || (NumSrc > 0 && (!srcpos || !nf))) return fail(C2RAY_ERR_ARG, "bad argument");
+  // srcpos indexes the mesh on the device (1-based, sourceprops_test.F90:93-106): anything else would make the sweep
+  // read and atomically add outside the grids.  Fluxes must be finite and non-negative (they scale every rate).
+  for (int i = 0; i < NumSrc; i++) {
+    for (int d = 0; d < 3; d++)
+      if (srcpos[3 * i + d] < 1 || srcpos[3 * i + d] > c->mesh[d])
+        return fail(C2RAY_ERR_ARG, "srcpos(" + std::to_string(d + 1) + "," + std::to_string(i + 1) + ") = " +
+                                       std::to_string(srcpos[3 * i + d]) + " outside 1..mesh (1-based mesh positions expected)");
+    const double f3[3] = {nf[i], nfpl ? nfpl[i] : 0.0, nfqpl ? nfqpl[i] : 0.0};
+    for (double f : f3)
+      if (!(f >= 0.0) || !std::isfinite(f))
+        return fail(C2RAY_ERR_ARG, "NormFlux of source " + std::to_string(i + 1) + " is negative or not finite");
+  }
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   for (double** p : {&c->d_nf, &c->d_nfpl, &c->d_nfqpl}) if (*p) { cudaFree(*p); *p = nullptr; }
@@ -1706,6 +1725,7 @@ int c2ray_b200_bench_global_pass(c2ray_ctx* c, double dt, int32_t reps, double* 
 }
 
 int64_t c2ray_b200_launch_count(c2ray_ctx* c) { return c ? c->launches : 0; }
+int64_t c2ray_b200_sweep_launch_count(c2ray_ctx* c) { return c ? c->sweep_launches : 0; }
 
 int c2ray_b200_measure_fp64(c2ray_ctx* c, double* tflops) {
   if (!c || !tflops) return fail(C2RAY_ERR_ARG, "null argument");

@@ -354,6 +354,9 @@ class C2Ray:
     def launch_count(self):
         return int(self.lib.c2ray_b200_launch_count(self.ctx))
 
+    def sweep_launch_count(self):
+        return int(self.lib.c2ray_b200_sweep_launch_count(self.ctx))
+
     def measure_fp64(self):
         t = C.c_double()
         capi.check(self.lib.c2ray_b200_measure_fp64(self.ctx, C.byref(t)))

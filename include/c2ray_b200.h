@@ -11,6 +11,13 @@
  * Every function returns 0 on success, a negative code otherwise; c2ray_b200_last_error() returns a
  * message.  There is no CPU fallback: without a CUDA device every compute entry point fails with
  * C2RAY_ERR_CUDA.
+ *
+ * Threading (the reference's routines are not re-entrant either: module globals, cgsconstants.f90:105-133): one
+ * context per process and device, driven from one host thread -- one MPI rank / one torchrun rank per GPU.  The
+ * per-run constants of the active context live in device __constant__ memory; two contexts alive on the same
+ * device must not have work in flight at the same time.  c2ray_b200_last_error() is per host thread.
+ * Arguments that become device indices are range-checked at the boundary: srcpos must lie in 1..mesh(d), the
+ * FreqBnd limits of uploaded tables in 1..47 (C2RAY_ERR_ARG otherwise).
  */
 #ifndef C2RAY_B200_H
 #define C2RAY_B200_H
@@ -240,6 +247,8 @@ int c2ray_b200_rates_device_buffer(c2ray_ctx* ctx, void** dptr, int64_t* count);
 int c2ray_b200_bench_global_pass(c2ray_ctx* ctx, double dt, int32_t reps, double* ms_per_pass, int32_t* conv_flag);
 /* kernels launched by this context since init (bench.py's gpu_launches) */
 int64_t c2ray_b200_launch_count(c2ray_ctx* ctx);
+/* launches of the ray-tracing kernel alone (the dominant kernel: bench.py's mean launch duration) */
+int64_t c2ray_b200_sweep_launch_count(c2ray_ctx* ctx);
 /* FP64 FMA throughput microbenchmark (TFLOP/s), for the FP64 roofline denominator */
 int c2ray_b200_measure_fp64(c2ray_ctx* ctx, double* tflops);
 /* CUDA-event stopwatch on the context's stream (device time of everything enqueued between the two calls) */

@@ -910,7 +910,9 @@ void cinterp(const Worker& W, const int* pos, const int* srcpos, double& cdensi,
 // ---------------------------------------------------------------------------------------------
 // evolve_point.F90:79-319 evolve0D  (niter /= -1 path; use_LLS=.false.)
 // ---------------------------------------------------------------------------------------------
-void evolve0D(Worker& W, const int* rtpos, int ns) {
+// loss_out / upd_out (parallel shell traversal only): the cell's photon-loss contribution and update count are handed
+// back instead of being accumulated in W, so that the caller can sum them in a fixed order.
+void evolve0D(Worker& W, const int* rtpos, int ns, double* loss_out = nullptr, long* upd_out = nullptr) {
   const double max_coldensh = F(2e29f);
   const int* mesh = G.mesh;
   const size_t N3 = ncell();
@@ -958,8 +960,13 @@ void evolve0D(Worker& W, const int* rtpos, int ns) {
     if (!G.isothermal) W.phiheat[p] = W.phiheat[p] + phi.heat;
     bool on_l = rtpos[0] == W.last_l[0] || rtpos[1] == W.last_l[1] || rtpos[2] == W.last_l[2];
     bool on_r = rtpos[0] == W.last_r[0] || rtpos[1] == W.last_r[1] || rtpos[2] == W.last_r[2];
-    if (on_l || on_r) W.photon_loss_src_thread = W.photon_loss_src_thread + phi.photo_out * G.vol / vol_ph;
-    W.updates++;
+    if (loss_out) {
+      if (on_l || on_r) *loss_out = phi.photo_out * G.vol / vol_ph;
+      *upd_out = 1;
+    } else {
+      if (on_l || on_r) W.photon_loss_src_thread = W.photon_loss_src_thread + phi.photo_out * G.vol / vol_ph;
+      W.updates++;
+    }
   }
 }
 
@@ -996,8 +1003,42 @@ void sweep_box_shell_order(Worker& W, int ns) {
         }
 }
 
+// The same shell-order traversal with the cells of one shell spread over `nthreads` OpenMP threads (cells of a shell
+// are independent, SURVEY H2: same-shell corners enter cinterp with weight exactly 0).  Per-cell results are
+// bitwise those of sweep_box_shell_order; the photon loss is summed in the same cell order afterwards.  Only there to
+// make single-source full-size parity runs (BASELINE configs[0]) finish in seconds.
+void sweep_box_shell_parallel(Worker& W, int ns, int nthreads) {
+  const int* sp = &G.srcpos[3 * (size_t)(ns - 1)];
+  int rmax = 0;
+  for (int d = 0; d < 3; d++) rmax = std::max(rmax, std::max(sp[d] - W.last_l[d], W.last_r[d] - sp[d]));
+  std::vector<int> cells;
+  std::vector<double> loss;
+  std::vector<long> upd;
+  for (int r = 0; r <= rmax; r++) {
+    cells.clear();
+    for (int dk = -r; dk <= r; dk++)
+      for (int dj = -r; dj <= r; dj++)
+        for (int di = -r; di <= r; di++) {
+          if (std::max(abs(di), std::max(abs(dj), abs(dk))) != r) continue;
+          const int rt[3] = {sp[0] + di, sp[1] + dj, sp[2] + dk};
+          bool in = true;
+          for (int d = 0; d < 3; d++) in = in && rt[d] >= W.last_l[d] && rt[d] <= W.last_r[d];
+          if (in) { cells.push_back(rt[0]); cells.push_back(rt[1]); cells.push_back(rt[2]); }
+        }
+    const long n = (long)cells.size() / 3;
+    loss.assign(n, 0.0); upd.assign(n, 0);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (long q = 0; q < n; q++) evolve0D(W, &cells[3 * q], ns, &loss[q], &upd[q]);
+    for (long q = 0; q < n; q++) {
+      if (loss[q] != 0.0) W.photon_loss_src_thread = W.photon_loss_src_thread + loss[q];
+      W.updates += upd[q];
+    }
+  }
+}
+
 // evolve_source.F90:66-238 do_source (serial branch, periodic_bc=.true.)
-int do_source(Worker& W, int ns, bool shell_order) {
+// shell_order: 0 reference serial order, 1 shell order, 2 shell order with `inner_threads` threads per shell
+int do_source(Worker& W, int ns, int shell_order, int inner_threads = 1) {
   const int* mesh = G.mesh;
   const int* sp = &G.srcpos[3 * (size_t)(ns - 1)];
   std::fill(W.cdh.begin(), W.cdh.end(), 0.0);
@@ -1022,7 +1063,9 @@ int do_source(Worker& W, int ns, bool shell_order) {
       W.last_r[d] = std::min(sp[d] + G.subboxsize * nbox, lastpos_r[d]);
       W.last_l[d] = std::max(sp[d] - G.subboxsize * nbox, lastpos_l[d]);
     }
-    if (shell_order) {
+    if (shell_order == 2) {
+      sweep_box_shell_parallel(W, ns, inner_threads);
+    } else if (shell_order == 1) {
       sweep_box_shell_order(W, ns);
     } else {
       int rtpos[3];
@@ -1379,18 +1422,28 @@ void orc_set_rates_to_zero() {
 
 // evolve.F90:385-431 pass_all_sources over the sources rank, rank+npr, ... (master_slave.F90:85 do_grid_static)
 // with nthreads OpenMP workers standing in for MPI ranks (private rate grids, summed in rank order afterwards:
-// evolve.F90:505-548).  order: 0 = reference serial sweep order, 1 = shell order.
+// evolve.F90:505-548).  order: 0 = reference serial sweep order, 1 = shell order, 2 = shell order with the threads
+// that the source loop leaves idle (fewer sources than threads) working inside each source's shells.
 // Returns the number of source x cell updates done.
 long orc_pass_all_sources(int nthreads, int order, int rank, int npr, int* nbox_per_source) {
   const size_t N3 = ncell();
   if (nthreads < 1) nthreads = 1;
+  std::vector<int> mine;
+  for (int ns1 = 1 + rank; ns1 <= G.NumSrc; ns1 += npr) mine.push_back(ns1);
+  int inner = 1;
+  if (order == 2) {  // workers = min(sources, threads); the rest of the threads go inside the shells
+    const int outer = std::max(1, std::min(nthreads, (int)mine.size()));
+    inner = std::max(1, nthreads / outer);
+    nthreads = outer;
+#ifdef _OPENMP
+    omp_set_max_active_levels(2);
+#endif
+  }
   if ((int)workers.size() != nthreads) setup_workers(nthreads);
   for (auto& W : workers) {
     W.photon_loss = 0; W.sum_nbox = 0; W.updates = 0;
     if (!W.own_rates.empty()) std::fill(W.own_rates.begin(), W.own_rates.end(), 0.0);
   }
-  std::vector<int> mine;
-  for (int ns1 = 1 + rank; ns1 <= G.NumSrc; ns1 += npr) mine.push_back(ns1);
 #pragma omp parallel for num_threads(nthreads) schedule(static, 1)
   for (int q = 0; q < (int)mine.size(); q++) {
 #ifdef _OPENMP
@@ -1398,7 +1451,7 @@ long orc_pass_all_sources(int nthreads, int order, int rank, int npr, int* nbox_
 #else
     int w = 0;
 #endif
-    int nb = do_source(workers[w], mine[q], order == 1);
+    int nb = do_source(workers[w], mine[q], order, inner);
     if (nbox_per_source) nbox_per_source[mine[q] - 1] = nb;
   }
   long upd = 0;
@@ -1570,6 +1623,14 @@ int orc_num_threads() {
   return omp_get_max_threads();
 #else
   return 1;
+#endif
+}
+
+// A launcher may have exported OMP_NUM_THREADS=1 for its children (torch.distributed.run does): the CPU arms of
+// bench.py set the thread count they state explicitly.
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
 #endif
 }
 

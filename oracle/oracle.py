@@ -253,3 +253,11 @@ def mrgrnk(x):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n=None):
+    """n=None: every CPU this process may run on (a launcher's OMP_NUM_THREADS=1 default is overridden)."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()

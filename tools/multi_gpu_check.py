@@ -8,8 +8,12 @@ For each of two consecutive evolve3D time steps it compares
       against the reference's scheme (allreduce of the rate grids + replicated pass, C2RAY_SPLIT_CHEM=0): bitwise at 2
       ranks in deterministic mode (a+b is the only sum), 1e-12 otherwise;
   (b) both against one rank tracing every source alone (tolerance: summation order of the rate grids);
-  (c) that every rank ends with the same full state and rate grids.
-Prints one line per rank and exits non-zero on a mismatch."""
+  (c) that every rank ends with the same full state and rate grids;
+  (d) the balanced source schedule against the static one, and a dump written under the split pass resuming bitwise;
+  (e) the NCCL-reduced rate grids of one source pass against the CPU oracle: every rank's own update count equals
+      orc_pass_all_sources(rank, npr) (do_grid_static, master_slave.F90:85), the reduced grids equal the oracle's pass
+      over all sources to 1e-8 relative (evolve.F90:505-548).
+Prints one line per rank and exits non-zero on a mismatch.  tests/test_gpu_multirank.py runs it under pytest."""
 import os
 import sys
 
@@ -68,6 +72,40 @@ def relerr(a, b):
     return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-300)))
 
 
+def oracle_check(p, local, uid, rank, world):
+    """(e): one source pass from a partially ionized state; NCCL allreduce vs the oracle."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from common import oracle_setup, oracle_grid, partially_ionized_state
+    tables = oracle_setup(p)
+    xh, xhe = partially_ionized_state(p, seed=3)
+    c = c2ray_b200.from_problem(p, device=local, tables=tables)
+    c.comm_init(uid, rank, world)
+    c.begin_step()
+    c.set_work_state(xh, xhe, xh, xhe)
+    c.set_rates_to_zero()
+    upd_mine = c.pass_all_sources(1, p["dt"])
+    rates = c.get_rates()
+    c.close()
+    g = oracle_grid(p)
+    g.set_work_state(xh, xhe, xh, xhe)
+    g.set_rates_to_zero()
+    upd_o_mine = g.pass_all_sources(rank=rank, npr=world)[0]
+    g.set_rates_to_zero()
+    upd_o_all = g.pass_all_sources()[0]
+    ref = g.get_rates()
+    err = 0.0
+    same_zero = True
+    for a, b in zip(rates, ref):
+        nz = b != 0.0
+        same_zero &= bool(np.array_equal(a != 0.0, nz))
+        if nz.any():
+            err = max(err, float(np.max(np.abs(a[nz] - b[nz]) / np.abs(b[nz]))))
+    tot = torch.tensor([upd_mine], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    ok = upd_mine == upd_o_mine and int(tot.item()) == upd_o_all and same_zero and err < 1e-8
+    return ok, err, upd_mine, upd_o_mine
+
+
 def main():
     mesh = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     nsrc = int(sys.argv[2]) if len(sys.argv) > 2 else 8
@@ -96,6 +134,8 @@ def main():
     dist.broadcast_object_list(tmp, src=0)
     restart_ok, restart_niter = run_dump_restart(p, local, uid, rank, world, tmp[0])
     ok = restart_ok
+    oracle_ok, oracle_err, upd_mine, upd_o_mine = oracle_check(p, local, uid(), rank, world)
+    ok &= oracle_ok
     # the balanced schedule: same integer histories, same fields to summation order, every source dealt exactly once
     counts = torch.zeros(len(p["NormFlux"]) + 1, dtype=torch.int32, device="cuda")
     counts[torch.tensor(mine_bal, dtype=torch.long, device="cuda")] += 1
@@ -143,6 +183,7 @@ def main():
           f"{ms(h_split)[0]:.1f}/{ms(h_split)[1]:.1f}/{ms(h_split)[2]:.1f} replicated {ms(h_repl)[0]:.1f}/{ms(h_repl)[1]:.1f}/{ms(h_repl)[2]:.1f}"
           f" | balanced schedule: sources {[int(x) for x in mine_static]} -> {[int(x) for x in mine_bal]}, err/tol {e_bal:.3f}"
           f" | dump+restart under the split pass (niter {restart_niter}) bitwise {restart_ok}"
+          f" | NCCL-reduced rates vs oracle: max rel {oracle_err:.2e}, own updates {upd_mine} == oracle(rank,npr) {upd_o_mine}: {oracle_ok}"
           f" -> {'OK' if ok else 'MISMATCH'}", flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
