@@ -139,26 +139,26 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------------------------
 class CpuSample:
     """The bounded CPU sample of a workload, on the oracle (the C++ restatement of the reference; the Fortran itself
-    cannot be built in this image).  Set-up, untimed: global iteration 1 of the time step over ALL sources from the
-    neutral start state (RT pass + global chemistry pass), so that the sample sees the ionized bubbles the GPU arm sees
-    for 24 of its 25 iterations.  One timed sample: the RT pass of iteration 2 over the workload's `k` brightest sources
-    (for configs[2] these are BB+QPL sources that trace the whole box -- the 50 such sources are 99 % of the GPU arm's
-    updates) with every host thread busy (sources over threads, idle threads inside a source's shells), plus the
-    k/NumSrc share of one global chemistry pass."""
+    cannot be built in this image).  The sample sources are the workload's `k` brightest (for configs[2] these are BB+QPL
+    sources that trace the whole box -- the 50 such sources are 99 % of the GPU arm's updates).  Set-up, untimed: global
+    iteration 1 of the time step for those k sources from the neutral start state (RT pass + global chemistry pass), so
+    that the timed passes see ionized bubbles around the sources like 11 of the GPU arm's 12 iterations do.  One timed
+    sample: the RT pass of iteration 2 over the k sources with every host thread busy (sources over threads, the threads
+    that leaves idle inside a source's shells), plus the k/NumSrc share of one global chemistry pass."""
 
     def __init__(self, name, p, nthreads):
         from oracle import oracle as O
         self.O, self.p, self.nthreads = O, p, nthreads
         w = WORKLOADS[name]
         self.ns_all = len(p["NormFlux"])
-        self.k = min(w["cpu_sample_sources"], self.ns_all)
+        self.k = k = min(w["cpu_sample_sources"], self.ns_all)
         O.rad_ini(p["T_eff"], p["S_star"], qpl=p.get("qpl"), isothermal=p["isothermal"])
         O.set_params(p["isothermal"], p["temper_val"], p["clumping"], p["zred"], p["H0"], p["Omega0"], p["cosmological"],
                      p["subboxsize"], p["max_subbox"])
         g = self.g = O.Grid(p["mesh"], p["dr"], p["vol"])
         g.set_state(p["ndens"], p["xh"], p["xhe"], p["temperature_grid"])
         q = p.get("NormFluxQPL")
-        g.set_sources(p["srcpos"], p["NormFlux"], None, q)
+        g.set_sources(p["srcpos"][:k], p["NormFlux"][:k], None, None if q is None else q[:k])
         g.set_work_state(p["xh"], p["xhe"], p["xh"], p["xhe"])
         g.set_rates_to_zero()
         t0 = time.perf_counter()
@@ -167,7 +167,6 @@ class CpuSample:
         g.global_pass(p["dt"], nthreads=nthreads)
         self.t_chem = time.perf_counter() - t1          # one global chemistry pass over the whole mesh
         self.t_setup = time.perf_counter() - t0
-        g.set_sources(p["srcpos"][:self.k], p["NormFlux"][:self.k], None, None if q is None else q[:self.k])
 
     def run(self):
         """-> (updates, seconds) of one sample."""
@@ -180,7 +179,7 @@ class CpuSample:
     def describe(self):
         n = int(self.p["mesh"][0])
         return (f"RT pass of global iteration 2 over the {self.k} brightest of the {self.ns_all} sources + {self.k}/{self.ns_all} of one "
-                f"global chemistry pass ({self.t_chem:.2f} s for the {n}^3 mesh), after an untimed iteration 1 over all sources "
+                f"global chemistry pass ({self.t_chem:.2f} s for the {n}^3 mesh), after an untimed iteration 1 of the same sources "
                 f"({self.t_setup:.1f} s); C++ restatement of the reference (oracle/, g++ -O2 -fopenmp), {self.nthreads} threads")
 
 

@@ -516,7 +516,11 @@ int sweep_all(c2ray_ctx* c) {
             // source at 128^3), costs 1 % at a full wave (redundant geometry)
             const bool split = c->sweep_split && cells * ngroups * 4 <= resident;
             const long long items = cells * (split ? SPLIT_LANES : 1);
+#if C2RAY_NOSTRIDE
+            const int blocks = (int)((items + 127) / 128);   // one work item per thread
+#else
             const int blocks = (int)std::min<long long>((items + 127) / 128, max_blocks);
+#endif
             // the predecessor in this group's stream is the previous shell of the same level (not k_decide): overlap
             // Measured: +6 % on a single source (one group: nothing else fills the draining tail), -0.7 % with two
             // groups on two streams (they already overlap each other's tails) -> only used with a single group.
@@ -929,7 +933,16 @@ static int pack_tables(c2ray_ctx* c, int s) {
   const int items = NumFreqBnd * PK_ROWS;
   LAUNCH(c, k_pack_tables, (items + 255) / 256, 256, c->tab[s][0], c->tab[s][1], c->tab[s][2], c->tab[s][3], c->packed[s]);
   CK(cudaGetLastError());
+  // optical depth beyond which a band of this SED reads only all-zero table rows (d_dead, c2ray_photo.cuh)
+  double* d_tmp = nullptr;
+  double dead[NumFreqBnd];
+  CK(cudaMalloc(&d_tmp, sizeof(dead)));
+  LAUNCH(c, k_band_dead, NumFreqBnd, 256, c->tab[s][0], c->tab[s][1], c->tab[s][2], c->tab[s][3], d_tmp);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dead, d_tmp, sizeof(dead), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d_tmp));
+  CK(cudaMemcpyToSymbol(d_dead, dead, sizeof(dead), (size_t)s * sizeof(dead)));
   return 0;
 }
 

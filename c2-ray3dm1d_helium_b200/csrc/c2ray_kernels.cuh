@@ -212,6 +212,9 @@ __global__ void k_cell_records_level(const Slot* __restrict__ slots, const int* 
 #ifndef C2RAY_SWEEP_MINBLOCKS
 #define C2RAY_SWEEP_MINBLOCKS 5
 #endif
+#ifndef C2RAY_NOSTRIDE
+#define C2RAY_NOSTRIDE 1   // one work item per thread (0: grid-stride loop over a capped grid)
+#endif
 #ifndef C2RAY_SWEEP_MINBLOCKS_MULTI
 #define C2RAY_SWEEP_MINBLOCKS_MULTI 5
 #endif
@@ -238,8 +241,12 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
   constexpr bool iso = ISO;
   const int m0 = d_run.mesh[0], m1 = d_run.mesh[1], m2 = d_run.mesh[2];
   unsigned int done = 0;
+#if C2RAY_NOSTRIDE
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, once = 1; once && t < total; once = 0) {
+#else
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
+#endif
     const long long item = LANES > 1 ? t / LANES : t;   // the LANES lanes of an aligned group share the item
     const int a = (int)(item / ncell);
     const int c = (int)(item - (long long)a * ncell);
@@ -359,7 +366,7 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     PhotOut phi = {0, 0, 0, 0, 0, 0};
     if (cin_H < max_coldensh) {  // :250-270
       double scale;
-      PhotAcc A = photoion_bands<ISO, MULTI, LANES>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, S.nflux, scale, lane_j);
+      PhotAcc A = photoion_bands<ISO, MULTI, LANES, false>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, S.nflux, scale, lane_j);
       if (LANES > 1) reduce_bands<ISO, LANES>(A, lane_mask);  // the branch above is uniform over the lanes of a cell
       // the cell's secondary-ionisation factors are only needed now: loading them after the band loop keeps twelve
       // registers free while it runs

@@ -23,6 +23,16 @@
 #pragma once
 #include "c2ray_physics.cuh"
 
+#ifndef C2RAY_LD256
+#define C2RAY_LD256 1
+#endif
+#ifndef C2RAY_TAUOUT_SUM
+#define C2RAY_TAUOUT_SUM 1
+#endif
+#ifndef C2RAY_DEAD_BANDS
+#define C2RAY_DEAD_BANDS 1
+#endif
+
 // tuning builds only: -DC2RAY_BAND_UNROLL=n unrolls the band loops
 #ifdef C2RAY_BAND_UNROLL
 #define C2_STR2(x) #x
@@ -51,6 +61,15 @@ constexpr size_t PK_TOTAL = PK_ISO_THIN_OFF + (size_t)NumFreqBnd * PK_ROWS;  // 
 // column_density.f90:351-376 with the fast reciprocal
 __device__ __forceinline__ double weightf_fast(double cd, double sig) { return fast_rcp(fmax(0.6, cd * sig)); }
 
+// Dead bands.  The table build zeroes every integrand with tau * (nu/nu_min)^-index >= 700 (radiation_tables.f90:607), so
+// beyond some row every entry of a band -- photo and heating, thick and thin -- is exactly 0.0 and the band contributes
+// exactly nothing to any rate of a cell whose incoming optical depth lies there (tau_out >= tau_in reads zero rows as
+// well).  d_dead[sed][band] is the optical depth of the row AFTER the first all-zero row of that SED's band (one row of
+// margin against the rounding of the table position), +inf for a band without such rows.  A band step returns before
+// its logarithms when tau_in >= d_dead: bit-identical results, and behind a thick neutral shell (an optical depth of
+// 40-70 per cell at the hydrogen edge on the 256^3 cosmological box) most low-energy bands are dead.
+__constant__ double d_dead[3][NumFreqBnd];
+
 struct TauPos { int ipos; double residual; };
 
 // radiation_photoionrates.f90:282-306: odpos = min(NumTau, max(0, 1+(log10(max(1e-20,tau))-minlogtau)/dlogtau)).
@@ -69,6 +88,13 @@ __device__ __forceinline__ TauPos tau_table_position(double tau) {
 // (ld.global.nc.L1::evict_last on these loads was tried: no change at 16 sources, 8 % slower at 1000 -- profiles/README.md)
 __device__ __forceinline__ double2 ld2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ double lerp(double a, double b, double t) { return fma(b - a, t, a); }  // :321-324
+// one packed table row (32 bytes) in one 256-bit load (sm_100: LDG.E.256)
+struct Row4 { double x, y, z, w; };
+__device__ __forceinline__ Row4 ld4(const double* p) {
+  Row4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
 
 struct PhotOut { double photo_HI, photo_HeI, photo_HeII, heat, photo_in, photo_out; };
 
@@ -120,17 +146,32 @@ struct CellCols {
 
 // One frequency band (1-based b, NSP species absorb in it) for every active SED.
 // MULTI = false: only the black-body SED exists in this run; NFlux is then factored out of the band loop.
-template <bool ISO, int NSP, bool MULTI>
+template <bool ISO, int NSP, bool MULTI, bool NEED_IN = true>
 __device__ __forceinline__ void band_step(int b, const CellCols& c, const double nflux[3], unsigned actmask,
-                                          PhotAcc& A, const double* __restrict__ pk_single = nullptr) {
+                                          PhotAcc& A, const double* __restrict__ pk_single = nullptr, int sed_single = 0) {
   const int q = b - 1;
   const double sHI = BANDREC(q).sigma_HI;
   const double sHeI = NSP >= 2 ? BANDREC(q).sigma_HeI : 0.0;
   const double sHeII = NSP == 3 ? BANDREC(q).sigma_HeII : 0.0;
+#if C2RAY_TAUOUT_SUM
+  // tau_out as tau_in + the cell's own optical depth (the sum the species shares below need anyway): 3 FP64
+  // operations fewer per band; differs from :172-183's direct sum by an ulp of tau_out
+  const double tcHI = c.cell_HI * sHI, tcHeI = NSP >= 2 ? c.cell_HeI * sHeI : 0.0, tcHeII = NSP == 3 ? c.cell_HeII * sHeII : 0.0;
+  double tau_in = c.in_HI * sHI;
+  if (NSP >= 2) tau_in = fma(c.in_HeI, sHeI, tau_in);
+  if (NSP == 3) tau_in = fma(c.in_HeII, sHeII, tau_in);
+  const double dtau = NSP == 3 ? (tcHI + tcHeI + tcHeII) : (NSP == 2 ? tcHI + tcHeI : tcHI);
+#if !defined(C2RAY_MULTI_SED_INNER) && C2RAY_DEAD_BANDS
+  if (tau_in >= d_dead[sed_single][q]) return;  // every table row this band would read is exactly zero
+#endif
+  const double tau_out = tau_in + dtau;
+#else
   double tau_in = c.in_HI * sHI, tau_out = c.out_HI * sHI;             // :172-183
   if (NSP >= 2) { tau_in = fma(c.in_HeI, sHeI, tau_in); tau_out = fma(c.out_HeI, sHeI, tau_out); }
   if (NSP == 3) { tau_in = fma(c.in_HeII, sHeII, tau_in); tau_out = fma(c.out_HeII, sHeII, tau_out); }
   const double dtau = tau_out - tau_in;
+  const double tcHI = c.cell_HI * sHI, tcHeI = c.cell_HeI * sHeI, tcHeII = c.cell_HeII * sHeII;
+#endif
   const bool thick_p = fabs(dtau) > d_lit[4];  // tau_photo_limit, :342
   const bool thick_h = fabs(dtau) > d_lit[5];  // tau_heat_limit, :482
   // both positions unconditionally: the two log10 evaluations are independent and interleave (the thin branch, which
@@ -138,10 +179,13 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
   const TauPos pin = tau_table_position(tau_in);
   const TauPos pout = tau_table_position(tau_out);
   // species shares of the band's absorption (:787-825) and per-species cell optical depths (:236-240)
-  const double tcHI = c.cell_HI * sHI, tcHeI = c.cell_HeI * sHeI, tcHeII = c.cell_HeII * sHeII;
   double scHI = 1.0, scHeI = 0.0, scHeII = 0.0;
   if (NSP == 3) {
+#if C2RAY_TAUOUT_SUM
+    const double f = fast_rcp(dtau);
+#else
     const double f = fast_rcp(tcHI + tcHeI + tcHeII);
+#endif
     scHI = tcHI * f; scHeI = tcHeI * f; scHeII = tcHeII * f;
   } else if (NSP == 2) {
     const double f = fast_rcp(tcHI + tcHeI);
@@ -173,7 +217,7 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
         phi_all = NFlux * dtau * lerp(__ldg(pt), __ldg(pt + 1), pin.residual);
         phi_out = phi_in - phi_all;
       }
-      A.a_in += phi_in;
+      if (NEED_IN) A.a_in += phi_in;
       A.a_out += phi_out;
       phot += phi_all;
       continue;
@@ -181,6 +225,38 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
     const double* ri = pk + row_in;
     const double* ro = pk + row_out;
     const double* ti = ri + PK_THIN_OFF;  // thin rows at tau_in
+#if C2RAY_LD256
+    if (NSP >= 2) {
+      // rows i and i+1 of the thick table at tau_in: [photo_thick, heat_thick HI, HeI, HeII] each, one 256-bit load per row
+      const Row4 i0 = ld4(ri), i1 = ld4(ri + PK_HALF);
+      const double phi_in = NFlux * lerp(i0.x, i1.x, pin.residual);  // photo_lookuptable :390-396
+      double phi_all, phi_out;
+      Row4 o0 = i0, o1 = i1;
+      if (thick_p) {
+        o0 = ld4(ro); o1 = ld4(ro + PK_HALF);
+        phi_out = NFlux * lerp(o0.x, o1.x, pout.residual);
+        phi_all = phi_in - phi_out;
+      } else {
+        const double thin = lerp(__ldg(ti), __ldg(ti + PK_HALF), pin.residual);
+        phi_all = NFlux * dtau * thin;
+        phi_out = phi_in - phi_all;
+      }
+      if (NEED_IN) A.a_in += phi_in;
+      A.a_out += phi_out;
+      phot += phi_all;
+      if (thick_h) {
+        ph_HI = fma(scHI, NFlux * (lerp(i0.y, i1.y, pin.residual) - lerp(o0.y, o1.y, pout.residual)), ph_HI);
+        ph_HeI = fma(scHeI, NFlux * (lerp(i0.z, i1.z, pin.residual) - lerp(o0.z, o1.z, pout.residual)), ph_HeI);
+        if (NSP == 3) ph_HeII = fma(scHeII, NFlux * (lerp(i0.w, i1.w, pin.residual) - lerp(o0.w, o1.w, pout.residual)), ph_HeII);
+      } else {
+        const Row4 t0 = ld4(ti), t1 = ld4(ti + PK_HALF);
+        ph_HI = fma(NFlux * tcHI, lerp(t0.y, t1.y, pin.residual), ph_HI);
+        ph_HeI = fma(NFlux * tcHeI, lerp(t0.z, t1.z, pin.residual), ph_HeI);
+        if (NSP == 3) ph_HeII = fma(NFlux * tcHeII, lerp(t0.w, t1.w, pin.residual), ph_HeII);
+      }
+      continue;
+    }
+#endif
     // thick values at tau_in: [photo_thick, heat_thick HI | heat_thick HeI, heat_thick HeII]
     const double2 i0a = ld2(ri), i1a = ld2(ri + PK_HALF);
     const double phi_in = NFlux * lerp(i0a.x, i1a.x, pin.residual);  // photo_lookuptable :390-396
@@ -195,7 +271,7 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
       phi_all = NFlux * dtau * thin;
       phi_out = phi_in - phi_all;
     }
-    A.a_in += phi_in;
+    if (NEED_IN) A.a_in += phi_in;
     A.a_out += phi_out;
     phot += phi_all;
     if (!ISO) {  // heat_lookuptable :586-760
@@ -248,7 +324,7 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
 // accumulators and the flux scale still to be applied (photoion_finish).
 // LANES > 1: the bands of a cell are dealt to LANES adjacent lanes of a warp (lane_j = 0..LANES-1 takes every
 // LANES-th band of each band group); the caller sums the accumulators over those lanes (reduce_bands).
-template <bool ISO, bool MULTI, int LANES = 1>
+template <bool ISO, bool MULTI, int LANES = 1, bool NEED_IN = true>
 __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, double in_HeI, double out_HeI,
                                                   double in_HeII, double out_HeII, const double nflux[3], double& scale_out,
                                                   int lane_j = 0) {
@@ -272,11 +348,11 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
       if (hi < lo || !(nf > 0.0)) continue;
       const double* __restrict__ pk = d_run.sed[s].packed;
       PhotAcc B = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-      if (lo <= NumBndin1 && lane_j == 0) band_step<ISO, 1, false>(1, c, nflux, 1u, B, pk);
+      if (lo <= NumBndin1 && lane_j == 0) band_step<ISO, 1, false, NEED_IN>(1, c, nflux, 1u, B, pk, s);
       for (int b = max(lo, NumBndin1 + 1) + lane_j; b <= min(hi, NumBndin1 + NumBndin2); b += LANES)
-        band_step<ISO, 2, false>(b, c, nflux, 1u, B, pk);
+        band_step<ISO, 2, false, NEED_IN>(b, c, nflux, 1u, B, pk, s);
       for (int b = max(lo, NumBndin1 + NumBndin2 + 1) + lane_j; b <= hi; b += LANES)
-        band_step<ISO, 3, false>(b, c, nflux, 1u, B, pk);
+        band_step<ISO, 3, false, NEED_IN>(b, c, nflux, 1u, B, pk, s);
       T.a_in = fma(nf, B.a_in, T.a_in); T.a_out = fma(nf, B.a_out, T.a_out);
       T.a_HI = fma(nf, B.a_HI, T.a_HI); T.a_HeI = fma(nf, B.a_HeI, T.a_HeI); T.a_HeII = fma(nf, B.a_HeII, T.a_HeII);
       if (!ISO) {
@@ -307,16 +383,16 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
   } else {
     blo = d_run.sed[0].lo; bhi = d_run.sed[0].hi;
     scale = nflux[0];
-    if (!(scale > 0.0)) bhi = 0;  // :207 if (NormFlux(nsrc) > 0.0)
+    // (scale == 0: every rate comes out as 0 x finite = 0, as :207 `if (NormFlux(nsrc) > 0.0)` would leave it)
   }
   PhotAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (blo <= NumBndin1 && bhi >= 1 && lane_j == 0) band_step<ISO, 1, MULTI>(1, c, nflux, act, A);
+  if (blo <= NumBndin1 && bhi >= 1 && lane_j == 0) band_step<ISO, 1, MULTI, NEED_IN>(1, c, nflux, act, A);
   C2_BAND_UNROLL
   for (int b = max(blo, NumBndin1 + 1) + lane_j; b <= min(bhi, NumBndin1 + NumBndin2); b += LANES)
-    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 2, MULTI>(b, c, nflux, act, A);
+    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 2, MULTI, NEED_IN>(b, c, nflux, act, A);
   C2_BAND_UNROLL
   for (int b = max(blo, NumBndin1 + NumBndin2 + 1) + lane_j; b <= bhi; b += LANES)
-    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 3, MULTI>(b, c, nflux, act, A);
+    if (!MULTI || ((bands >> (b - 1)) & 1ull)) band_step<ISO, 3, MULTI, NEED_IN>(b, c, nflux, act, A);
   scale_out = scale;
   return A;
 }
@@ -391,6 +467,34 @@ __global__ void k_pack_tables(const double* __restrict__ photo_thick, const doub
   }
   packed[PK_ISO_OFF + t] = v[0];
   packed[PK_ISO_THIN_OFF + t] = v[PK_HALF];
+}
+
+// First all-zero row of every band of one SED's tables -> optical depth from which the band is dead (see d_dead).
+// One block per band; tables as the host holds them: (0:NumTau, 1:nb), band-major.
+__global__ void k_band_dead(const double* __restrict__ photo_thick, const double* __restrict__ photo_thin,
+                            const double* __restrict__ heat_thick, const double* __restrict__ heat_thin,
+                            double* __restrict__ dead_tau) {
+  const int q = blockIdx.x, b = q + 1;
+  const int nsp = (b <= NumBndin1) ? 1 : (b <= NumBndin1 + NumBndin2 ? 2 : 3);
+  const int hcol = (b <= NumBndin1) ? 0 : (b <= NumBndin1 + NumBndin2 ? 2 * b - NumBndin1 - 2 : 3 * b - NumBndin2 - NumBndin1 * 2 - 3);
+  __shared__ int last_nonzero;
+  if (threadIdx.x == 0) last_nonzero = -1;
+  __syncthreads();
+  int mine = -1;
+  for (int it = threadIdx.x; it <= NumTau; it += blockDim.x) {
+    bool nz = photo_thick[(size_t)q * (NumTau + 1) + it] != 0.0 || photo_thin[(size_t)q * (NumTau + 1) + it] != 0.0;
+    if (heat_thick && heat_thin)
+      for (int sp = 0; sp < nsp; sp++)
+        nz = nz || heat_thick[(size_t)(hcol + sp) * (NumTau + 1) + it] != 0.0 || heat_thin[(size_t)(hcol + sp) * (NumTau + 1) + it] != 0.0;
+    if (nz) mine = max(mine, it);
+  }
+  atomicMax(&last_nonzero, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int first_zero = last_nonzero + 1, row = first_zero + 1;   // one row of margin
+    // row i >= 1 of the table is tau = 10^(minlogtau + dlogtau (i-1)) (radiation_tables.f90:181-186)
+    dead_tau[q] = row <= NumTau ? pow(10.0, minlogtau + dlogtau * (double)(row - 1)) : __longlong_as_double(0x7ff0000000000000LL);
+  }
 }
 
 }  // namespace c2

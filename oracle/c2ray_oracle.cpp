@@ -985,22 +985,38 @@ void evolve2D(Worker& W, int* rtpos, int ns) {
   }
 }
 
+// Offsets of max-norm shell r in ascending (dk, dj, di) order, O(r^2) per shell.
+template <class Fn>
+inline void for_each_shell_offset(int r, Fn fn) {
+  for (int dk = -r; dk <= r; dk++) {
+    if (abs(dk) == r) {
+      for (int dj = -r; dj <= r; dj++)
+        for (int di = -r; di <= r; di++) fn(di, dj, dk);
+    } else {
+      for (int dj = -r; dj <= r; dj++) {
+        if (abs(dj) == r) {
+          for (int di = -r; di <= r; di++) fn(di, dj, dk);
+        } else {
+          fn(-r, dj, dk);
+          fn(r, dj, dk);  // r > 0 here (|dk| < r)
+        }
+      }
+    }
+  }
+}
+
 // Shell-order traversal of the current sub-box (the wavefront order the GPU uses); SURVEY H2.
 void sweep_box_shell_order(Worker& W, int ns) {
   const int* sp = &G.srcpos[3 * (size_t)(ns - 1)];
   int rmax = 0;
   for (int d = 0; d < 3; d++) rmax = std::max(rmax, std::max(sp[d] - W.last_l[d], W.last_r[d] - sp[d]));
-  int rtpos[3];
   for (int r = 0; r <= rmax; r++)
-    for (int dk = -r; dk <= r; dk++)
-      for (int dj = -r; dj <= r; dj++)
-        for (int di = -r; di <= r; di++) {
-          if (std::max(abs(di), std::max(abs(dj), abs(dk))) != r) continue;
-          rtpos[0] = sp[0] + di; rtpos[1] = sp[1] + dj; rtpos[2] = sp[2] + dk;
-          bool in = true;
-          for (int d = 0; d < 3; d++) in = in && rtpos[d] >= W.last_l[d] && rtpos[d] <= W.last_r[d];
-          if (in) evolve0D(W, rtpos, ns);
-        }
+    for_each_shell_offset(r, [&](int di, int dj, int dk) {
+      int rtpos[3] = {sp[0] + di, sp[1] + dj, sp[2] + dk};
+      bool in = true;
+      for (int d = 0; d < 3; d++) in = in && rtpos[d] >= W.last_l[d] && rtpos[d] <= W.last_r[d];
+      if (in) evolve0D(W, rtpos, ns);
+    });
 }
 
 // The same shell-order traversal with the cells of one shell spread over `nthreads` OpenMP threads (cells of a shell
@@ -1016,15 +1032,12 @@ void sweep_box_shell_parallel(Worker& W, int ns, int nthreads) {
   std::vector<long> upd;
   for (int r = 0; r <= rmax; r++) {
     cells.clear();
-    for (int dk = -r; dk <= r; dk++)
-      for (int dj = -r; dj <= r; dj++)
-        for (int di = -r; di <= r; di++) {
-          if (std::max(abs(di), std::max(abs(dj), abs(dk))) != r) continue;
-          const int rt[3] = {sp[0] + di, sp[1] + dj, sp[2] + dk};
-          bool in = true;
-          for (int d = 0; d < 3; d++) in = in && rt[d] >= W.last_l[d] && rt[d] <= W.last_r[d];
-          if (in) { cells.push_back(rt[0]); cells.push_back(rt[1]); cells.push_back(rt[2]); }
-        }
+    for_each_shell_offset(r, [&](int di, int dj, int dk) {
+      const int rt[3] = {sp[0] + di, sp[1] + dj, sp[2] + dk};
+      bool in = true;
+      for (int d = 0; d < 3; d++) in = in && rt[d] >= W.last_l[d] && rt[d] <= W.last_r[d];
+      if (in) { cells.push_back(rt[0]); cells.push_back(rt[1]); cells.push_back(rt[2]); }
+    });
     const long n = (long)cells.size() / 3;
     loss.assign(n, 0.0); upd.assign(n, 0);
 #pragma omp parallel for num_threads(nthreads) schedule(static)
@@ -1437,6 +1450,7 @@ long orc_pass_all_sources(int nthreads, int order, int rank, int npr, int* nbox_
     nthreads = outer;
 #ifdef _OPENMP
     omp_set_max_active_levels(2);
+    omp_set_nested(1);  // older libgomp builds (the copy bundled with torch wins when torch was imported first) need this one
 #endif
   }
   if ((int)workers.size() != nthreads) setup_workers(nthreads);

@@ -297,7 +297,9 @@ def thermal_py(dt, T, ne, n, ion, heat, coolin, cosmo):
     return T_end, avg
 
 
-def do_chemistry_py(dt, n, ion15, phi4, T_avg_in, T_old, coolin, cosmo, isothermal):
+def do_chemistry_py(dt, n, ion15, phi4, T_avg_in, T_old, coolin, cosmo, isothermal, doric=None):
+    """doric: callable(dt, de, n, ion15, phi3, fr4, T) -> ion15; default: the oracle's single-call hook."""
+    doric = doric or O.doric
     ion = np.array(ion15, dtype=np.float64)
     sig = dict(H_heth=1.238e-18, H_heLya=9.907e-22, He_heLya=1.301e-20, He_he2=1.690780687052975e-18,
                H_he2=1.230695924714239e-19, HeI=F(7.430e-18), HeII=F(1.589e-18))
@@ -317,11 +319,11 @@ def do_chemistry_py(dt, n, ion15, phi4, T_avg_in, T_old, coolin, cosmo, isotherm
         temper2 = temper1
         yh0, yhe0, yhe2 = ion[5], ion[7], ion[9]
         de = electrondens_py(n, ion[5:7], ion[7:10])
-        ion = O.doric(dt, de, n, ion, phi4[:3], fracs(), avg_temper)
+        ion = doric(dt, de, n, ion, phi4[:3], fracs(), avg_temper)
         de = electrondens_py(n, ion[5:7], ion[7:10])
         fr = fracs()
         old = ion.copy()
-        ion = O.doric(dt, de, n, ion, phi4[:3], fr, avg_temper)
+        ion = doric(dt, de, n, ion, phi4[:3], fr, avg_temper)
         for q in (0, 1, 2, 3, 4, 5, 7, 8):                       # h(0:1) he(0:2) h_av(0) he_av(0:1); h_av(1), he_av(2) keep pass 2
             ion[q] = (ion[q] + old[q]) / 2.0
         de = electrondens_py(n, ion[5:7], ion[7:10])
