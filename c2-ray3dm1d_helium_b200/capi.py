@@ -18,7 +18,7 @@ EXPORTS = [
     "c2ray_b200_snapshot_state", "c2ray_b200_restore_state", "c2ray_b200_evolve3d", "c2ray_b200_evolve3d_host",
     "c2ray_b200_begin_step", "c2ray_b200_set_rates_to_zero", "c2ray_b200_pass_all_sources", "c2ray_b200_do_source",
     "c2ray_b200_global_pass", "c2ray_b200_end_step", "c2ray_b200_state_sums", "c2ray_b200_photoion_rates_batch",
-    "c2ray_b200_chemistry_batch", "c2ray_b200_rec_colion_batch", "c2ray_b200_cinterp_batch",
+    "c2ray_b200_chemistry_batch", "c2ray_b200_doric_batch", "c2ray_b200_thermal_batch", "c2ray_b200_rec_colion_batch", "c2ray_b200_cinterp_batch",
     "c2ray_b200_comm_unique_id", "c2ray_b200_comm_init", "c2ray_b200_set_rank", "c2ray_b200_rates_device_buffer",
     "c2ray_b200_bench_global_pass", "c2ray_b200_launch_count", "c2ray_b200_sweep_launch_count", "c2ray_b200_measure_fp64", "c2ray_b200_stream",
     "c2ray_b200_timer_start", "c2ray_b200_timer_stop",

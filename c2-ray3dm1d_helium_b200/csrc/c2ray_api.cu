@@ -131,6 +131,8 @@ struct c2ray_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_SWEEP_GROUPS] = {};
   int sweep_groups = 2;                     // env C2RAY_SWEEP_GROUPS
   int sweep_split = 1;                      // env C2RAY_SWEEP_SPLIT: band-split kernel for launches that cannot fill the GPU
+  int sweep_lanes_mode = 1;                 // env C2RAY_SWEEP_LANES_MODE: 1 graded 2..16 lanes per cell, 0 the 8-lanes-or-1 rule
+  double sweep_lanes_fill = 1.0;            // env C2RAY_SWEEP_LANES_FILL: resident waves the split threads may fill
   int sparse_records = 1;                   // env C2RAY_SPARSE_RECORDS: per-level cell records when the sources cover little of the mesh
   long long last_pass_updates = -1;         // updates of this rank's previous pass (-1: none yet)
   int sweep_pdl = 1;                        // env C2RAY_SWEEP_PDL: programmatic dependent launch between the shells of a level
@@ -142,6 +144,7 @@ struct c2ray_ctx {
   double* d_sums = nullptr;
   double* d_cellrec = nullptr;  // per-cell sweep inputs, rebuilt every iteration (k_cell_records)
   unsigned long long* d_next_cell = nullptr;
+  BandRec h_band[NumFreqBnd];  // host copy of the band records in constant memory
   int n_sm = 148;          // multiprocessors of this context's device
   int chemq_per_sm = 0;    // resident CTAs per SM of k_global_pass_q (queried once per context)
   int chem_mode = -1;      // -1 auto, 0 one cell per thread, 1 queue-driven (env C2RAY_CHEM_QUEUE overrides)
@@ -219,8 +222,8 @@ int bind(c2ray_ctx* c) {
 }
 
 int upload_band_const(c2ray_ctx* c) {
-  BandRec bc[NumFreqBnd];
-  memset(bc, 0, sizeof(bc));
+  BandRec* bc = c->h_band;
+  memset(bc, 0, sizeof(c->h_band));
   bc[0].sigma_HI = sigma_HI_at_ion_freq;  // radiation_sizes.f90:381-383
   for (int i = 0; i < 26; i++) {
     const int q = NumBndin1 + i;
@@ -238,7 +241,8 @@ int upload_band_const(c2ray_ctx* c) {
     bc[q].f1heat_HI = BD_F1HEAT_HI_B3[i]; bc[q].f1heat_HeI = BD_F1HEAT_HEI_B3[i]; bc[q].f1heat_HeII = BD_F1HEAT_HEII_B3[i];
     bc[q].f2heat_HI = BD_F2HEAT_HI_B3[i]; bc[q].f2heat_HeI = BD_F2HEAT_HEI_B3[i]; bc[q].f2heat_HeII = BD_F2HEAT_HEII_B3[i];
   }
-  CK(cudaMemcpyToSymbol(d_band, bc, sizeof(bc)));
+  for (int q = 0; q < NumFreqBnd; q++) bc[q].dead_bb = INFINITY;  // until tables are packed (pack_tables)
+  CK(cudaMemcpyToSymbol(d_band, bc, sizeof(c->h_band)));
   return 0;
 }
 
@@ -510,12 +514,20 @@ int sweep_all(c2ray_ctx* c) {
           for (int q = 0; q < ngroups; q++) {
             if (nact[q] <= 0) continue;
             const long long cells = (long long)nact[q] * (r == 0 ? 1 : 24LL * r * r + 2);
-            // fewer cells than resident threads: latency bound, SPLIT_LANES lanes share a cell (see k_sweep_shell)
+            // Fewer cells than resident threads: the launch is bound by the latency of one update's dependency chain,
+            // not by throughput, so 2..16 lanes share a cell (see k_sweep_shell) -- as many as still fit the resident
+            // threads (x sweep_lanes_fill).  sweep_lanes_mode 0: the round-1 rule (8 lanes below a quarter wave).
             const long long resident = 148LL * 128 * (multi_sed ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS);
-            // measured: pays off below a quarter of the resident threads (12 % on 1250 sources x r <= 10, 9 % on one
-            // source at 128^3), costs 1 % at a full wave (redundant geometry)
-            const bool split = c->sweep_split && cells * ngroups * 4 <= resident;
-            const long long items = cells * (split ? SPLIT_LANES : 1);
+            int lanes = 1;
+            if (c->sweep_split) {
+              if (c->sweep_lanes_mode == 0) {
+                if (cells * ngroups * 4 <= resident) lanes = SPLIT_LANES;
+              } else {
+                for (int L = 16; L >= 2; L >>= 1)
+                  if ((double)(cells * ngroups * L) <= c->sweep_lanes_fill * (double)resident) { lanes = L; break; }
+              }
+            }
+            const long long items = cells * lanes;
 #if C2RAY_NOSTRIDE
             const int blocks = (int)((items + 127) / 128);   // one work item per thread
 #else
@@ -532,7 +544,16 @@ int sweep_all(c2ray_ctx* c) {
                          c->d_scratch + (size_t)goff[q] * slot_stride, r));                                                   \
     c->launches++; c->sweep_launches++;                                                                                        \
   } while (0)
-#define SWEEP2(ISO, MULTI) do { if (split) SWEEP(ISO, MULTI, SPLIT_LANES); else SWEEP(ISO, MULTI, 1); } while (0)
+#define SWEEP2(ISO, MULTI)                         \
+  do {                                             \
+    switch (lanes) {                               \
+      case 16: SWEEP(ISO, MULTI, 16); break;       \
+      case 8: SWEEP(ISO, MULTI, 8); break;         \
+      case 4: SWEEP(ISO, MULTI, 4); break;         \
+      case 2: SWEEP(ISO, MULTI, 2); break;         \
+      default: SWEEP(ISO, MULTI, 1); break;        \
+    }                                              \
+  } while (0)
             if (multi_sed) { if (c->par.isothermal) SWEEP2(true, true); else SWEEP2(false, true); }
             else { if (c->par.isothermal) SWEEP2(true, false); else SWEEP2(false, false); }
 #undef SWEEP2
@@ -863,6 +884,8 @@ static int init_device_state(c2ray_ctx* c) {
   for (auto& ev : c->ev_join) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   if (const char* e = getenv("C2RAY_SWEEP_SPLIT")) c->sweep_split = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_PDL")) c->sweep_pdl = atoi(e);
+  if (const char* e = getenv("C2RAY_SWEEP_LANES_MODE")) c->sweep_lanes_mode = atoi(e);
+  if (const char* e = getenv("C2RAY_SWEEP_LANES_FILL")) c->sweep_lanes_fill = std::max(0.1, atof(e));
   if (const char* e = getenv("C2RAY_SPARSE_RECORDS")) c->sparse_records = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_GROUPS")) c->sweep_groups = std::max(1, std::min(MAX_SWEEP_GROUPS, atoi(e)));
   CK(cudaMalloc(&c->d_chem, sizeof(ChemTotals)));
@@ -943,6 +966,10 @@ static int pack_tables(c2ray_ctx* c, int s) {
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaFree(d_tmp));
   CK(cudaMemcpyToSymbol(d_dead, dead, sizeof(dead), (size_t)s * sizeof(dead)));
+  if (s == 0) {
+    for (int q = 0; q < NumFreqBnd; q++) c->h_band[q].dead_bb = dead[q];
+    CK(cudaMemcpyToSymbol(d_band, c->h_band, sizeof(c->h_band)));
+  }
   return 0;
 }
 
@@ -1577,6 +1604,56 @@ int c2ray_b200_chemistry_batch(c2ray_ctx* c, int32_t n, double dt, const double*
   CK(cudaMemcpy(T3, d_T, 24 * (size_t)n, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(nit_out, d_nit, 4 * (size_t)n, cudaMemcpyDeviceToHost));
   cudaFree(d_n); cudaFree(d_ion); cudaFree(d_phi); cudaFree(d_T); cudaFree(d_nit);
+  return C2RAY_OK;
+}
+
+int c2ray_b200_doric_batch(c2ray_ctx* c, int32_t n, double dt, const double* rhe, double* ion15, const double* phi3,
+                           const double* fr4, const double* T) {
+  if (!c || n <= 0 || !rhe || !ion15 || !phi3 || !fr4 || !T) return fail(C2RAY_ERR_ARG, "bad argument");
+  int rc = bind(c);
+  if (rc) return rc;
+  const size_t N = (size_t)n;
+  double* d = nullptr;   // [rhe | ion15 | phi3 | fr4 | T]
+  CK(cudaMalloc(&d, 8 * N * (1 + 15 + 3 + 4 + 1)));
+  double *d_rhe = d, *d_ion = d + N, *d_phi = d_ion + 15 * N, *d_fr = d_phi + 3 * N, *d_T = d_fr + 4 * N;
+  CK(cudaMemcpy(d_rhe, rhe, 8 * N, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_ion, ion15, 120 * N, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_phi, phi3, 24 * N, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_fr, fr4, 32 * N, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_T, T, 8 * N, cudaMemcpyHostToDevice));
+  LAUNCH(c, k_doric_batch, (n + 127) / 128, 128, n, dt, d_rhe, d_ion, d_phi, d_fr, d_T);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(ion15, d_ion, 120 * N, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return C2RAY_OK;
+}
+
+int c2ray_b200_thermal_batch(c2ray_ctx* c, int32_t n, double dt, double* end_temper, double* avg_temper, const double* ne,
+                             const double* ndens, const double* ion15, const double* heat, int32_t* nsub) {
+  if (!c || n <= 0 || !end_temper || !avg_temper || !ne || !ndens || !ion15 || !heat || !nsub) return fail(C2RAY_ERR_ARG, "bad argument");
+  int rc = bind(c);
+  if (rc) return rc;
+  if (!c->have_cool) return fail(C2RAY_ERR_STATE, "cooling tables not set");
+  const size_t N = (size_t)n;
+  double* d = nullptr;   // [end | avg | ne | ndens | heat | ion15]
+  int* d_ns = nullptr;
+  CK(cudaMalloc(&d, 8 * N * (5 + 15)));
+  CK(cudaMalloc(&d_ns, 4 * N));
+  double *d_e = d, *d_a = d + N, *d_ne = d + 2 * N, *d_n = d + 3 * N, *d_h = d + 4 * N, *d_ion = d + 5 * N;
+  CK(cudaMemcpy(d_e, end_temper, 8 * N, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_a, avg_temper, 8 * N, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_ne, ne, 8 * N, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_n, ndens, 8 * N, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_h, heat, 8 * N, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_ion, ion15, 120 * N, cudaMemcpyHostToDevice));
+  LAUNCH(c, k_thermal_batch, (n + 127) / 128, 128, n, dt, d_e, d_a, d_ne, d_n, d_ion, d_h, d_ns);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(end_temper, d_e, 8 * N, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(avg_temper, d_a, 8 * N, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(nsub, d_ns, 4 * N, cudaMemcpyDeviceToHost));
+  cudaFree(d); cudaFree(d_ns);
   return C2RAY_OK;
 }
 

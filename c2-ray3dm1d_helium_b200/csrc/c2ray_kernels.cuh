@@ -752,6 +752,41 @@ __global__ void k_chemistry_batch(int n, double dt, const double* __restrict__ n
   nit_out[t] = nit;
 }
 
+// doric.f90:35-313 alone, coefficients from ini_rec_colion_factors(T[t]) (cgsconstants.f90:140): one call per state
+__global__ void k_doric_batch(int n, double dt, const double* __restrict__ rhe, double* __restrict__ ion15,
+                              const double* __restrict__ phi3, const double* __restrict__ fr4, const double* __restrict__ T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double* v = ion15 + 15 * (size_t)t;
+  Ion ion;
+  ion.h0 = v[0]; ion.h1 = v[1]; ion.he0 = v[2]; ion.he1 = v[3]; ion.he2 = v[4];
+  ion.h_av0 = v[5]; ion.h_av1 = v[6]; ion.he_av0 = v[7]; ion.he_av1 = v[8]; ion.he_av2 = v[9];
+  ion.h_old0 = v[10]; ion.h_old1 = v[11]; ion.he_old0 = v[12]; ion.he_old1 = v[13]; ion.he_old2 = v[14];
+  RecCol rc;
+  ini_rec_colion_factors(T[t], rc);
+  DoricFrac fr;
+  fr.y = fr4[4 * t]; fr.z = fr4[4 * t + 1]; fr.y2a = fr4[4 * t + 2]; fr.y2b = fr4[4 * t + 3];
+  doric(dt, rhe[t], ion, phi3[3 * t], phi3[3 * t + 1], phi3[3 * t + 2], fr, rc, d_run.clumping);
+  v[0] = ion.h0; v[1] = ion.h1; v[2] = ion.he0; v[3] = ion.he1; v[4] = ion.he2;
+  v[5] = ion.h_av0; v[6] = ion.h_av1; v[7] = ion.he_av0; v[8] = ion.he_av1; v[9] = ion.he_av2;
+}
+
+// thermal.f90:22-174 alone: end_temper in/out, avg_temper in/out (untouched at or below minitemp), sub-step count out
+__global__ void k_thermal_batch(int n, double dt, double* __restrict__ end_temper, double* __restrict__ avg_temper,
+                                const double* __restrict__ ne, const double* __restrict__ ndens,
+                                const double* __restrict__ ion15, const double* __restrict__ heat, int* __restrict__ nsub) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double* v = ion15 + 15 * (size_t)t;
+  Ion ion;
+  ion.h0 = v[0]; ion.h1 = v[1]; ion.he0 = v[2]; ion.he1 = v[3]; ion.he2 = v[4];
+  ion.h_av0 = v[5]; ion.h_av1 = v[6]; ion.he_av0 = v[7]; ion.he_av1 = v[8]; ion.he_av2 = v[9];
+  ion.h_old0 = v[10]; ion.h_old1 = v[11]; ion.he_old0 = v[12]; ion.he_old1 = v[13]; ion.he_old2 = v[14];
+  double e = end_temper[t], a = avg_temper[t];
+  nsub[t] = thermal(dt, e, a, ne[t], ndens[t], ion, heat[t]);
+  end_temper[t] = e; avg_temper[t] = a;
+}
+
 __global__ void k_rec_colion_batch(int n, const double* __restrict__ T, double* __restrict__ out12) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;

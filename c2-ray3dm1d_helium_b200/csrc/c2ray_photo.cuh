@@ -162,7 +162,8 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
   if (NSP == 3) tau_in = fma(c.in_HeII, sHeII, tau_in);
   const double dtau = NSP == 3 ? (tcHI + tcHeI + tcHeII) : (NSP == 2 ? tcHI + tcHeI : tcHI);
 #if !defined(C2RAY_MULTI_SED_INNER) && C2RAY_DEAD_BANDS
-  if (tau_in >= d_dead[sed_single][q]) return;  // every table row this band would read is exactly zero
+  // (the single-SED kernels read the black body's threshold from the band record they have in cache anyway)
+  if (tau_in >= (pk_single ? d_dead[sed_single][q] : BANDREC(q).dead_bb)) return;  // every row this band would read is exactly zero
 #endif
   const double tau_out = tau_in + dtau;
 #else

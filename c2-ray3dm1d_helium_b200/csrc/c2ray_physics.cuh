@@ -53,7 +53,7 @@ struct BandRec {
   double f2ion_HI, f2ion_HeI, f2ion_HeII;
   double f1heat_HI, f1heat_HeI, f1heat_HeII;
   double f2heat_HI, f2heat_HeI, f2heat_HeII;
-  double pad;
+  double dead_bb;  // optical depth from which the black-body tables of this band are all zero (d_dead, c2ray_photo.cuh)
 };
 
 struct RunConst {

@@ -291,6 +291,25 @@ class C2Ray:
                                                        _p(_f64(phi4)), _p(T), _p(nit)))
         return ion, T, nit
 
+    def doric(self, dt, rhe, ion15, phi3, fr4, T):
+        """doric.f90:35 for n states (coefficients at T per state); returns the updated ion15[n][15]."""
+        rhe = _f64(np.atleast_1d(rhe)); n = len(rhe)
+        ion = np.array(ion15, dtype=np.float64).reshape(n, 15).copy()
+        capi.check(self.lib.c2ray_b200_doric_batch(self.ctx, C.c_int32(n), C.c_double(dt), _p(rhe), _p(ion),
+                                                   _p(_f64(np.reshape(phi3, (n, 3)))), _p(_f64(np.reshape(fr4, (n, 4)))),
+                                                   _p(_f64(np.atleast_1d(T)))))
+        return ion
+
+    def thermal(self, dt, end_temper, avg_temper, ndens_electron, ndens_atom, ion15, heat):
+        """thermal.f90:22 for n states; returns (end_temper, avg_temper, sub-steps)."""
+        e = np.array(np.atleast_1d(end_temper), dtype=np.float64); n = len(e)
+        a = np.array(np.atleast_1d(avg_temper), dtype=np.float64)
+        ns = np.zeros(n, dtype=np.int32)
+        capi.check(self.lib.c2ray_b200_thermal_batch(self.ctx, C.c_int32(n), C.c_double(dt), _p(e), _p(a),
+                                                     _p(_f64(np.atleast_1d(ndens_electron))), _p(_f64(np.atleast_1d(ndens_atom))),
+                                                     _p(_f64(np.reshape(ion15, (n, 15)))), _p(_f64(np.atleast_1d(heat))), _p(ns)))
+        return e, a, ns
+
     def ini_rec_colion_factors(self, T):
         T = _f64(np.atleast_1d(T))
         out = np.zeros((len(T), 12))

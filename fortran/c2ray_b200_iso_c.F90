@@ -213,6 +213,11 @@ contains
          bb_FreqBnd_LowerLimit, bb_FreqBnd_UpperLimit
     use radiation_sed_parameters, only: S_star
     use file_admin, only: dump_dir
+#ifdef PL
+    use radiation_tables, only: pl_photo_thick_table, pl_photo_thin_table, pl_heat_thick_table, &
+         pl_heat_thin_table, pl_FreqBnd_LowerLimit, pl_FreqBnd_UpperLimit
+    use radiation_sed_parameters, only: pl_S_star
+#endif
 #ifdef QUASARS
     use radiation_tables, only: qpl_photo_thick_table, qpl_photo_thin_table, qpl_heat_thick_table, &
          qpl_heat_thin_table, qpl_FreqBnd_LowerLimit, qpl_FreqBnd_UpperLimit
@@ -256,6 +261,19 @@ contains
     tab%freqbnd_upper = bb_FreqBnd_UpperLimit
     tab%S_star = S_star
     call check(c2ray_b200_upload_tables(ctx, 0_c_int32_t, tab), "upload_tables(B)")
+#ifdef PL
+    ! the power-law SED "P" (radiation_photoionrates.f90:214-220 reads these tables with NormFluxPL): sed index 1
+    tab%photo_thick = c_loc(pl_photo_thick_table)
+    tab%photo_thin = c_loc(pl_photo_thin_table)
+    if (.not.isothermal) then
+       tab%heat_thick = c_loc(pl_heat_thick_table)
+       tab%heat_thin = c_loc(pl_heat_thin_table)
+    endif
+    tab%freqbnd_lower = pl_FreqBnd_LowerLimit
+    tab%freqbnd_upper = pl_FreqBnd_UpperLimit
+    tab%S_star = pl_S_star
+    call check(c2ray_b200_upload_tables(ctx, 1_c_int32_t, tab), "upload_tables(P)")
+#endif
 #ifdef QUASARS
     tab%photo_thick = c_loc(qpl_photo_thick_table)
     tab%photo_thin = c_loc(qpl_photo_thin_table)
@@ -268,7 +286,6 @@ contains
     tab%S_star = qpl_S_star
     call check(c2ray_b200_upload_tables(ctx, 2_c_int32_t, tab), "upload_tables(Q)")
 #endif
-    ! (-DPL: same with the pl_* arrays and sed index 1)
 
     ! iteration dumps every 15 minutes into dump_dir, as evolve.F90:199-213 does; evolve3D's restart flag then finds
     ! iterdump1.bin / iterdump2.bin / iterdump.bin there (evolve.F90:279 start_from_dump)
@@ -305,17 +322,24 @@ contains
   !> After sourceprops has (re)built the source list.
   subroutine c2ray_b200_new_sources()
     use sourceprops, only: NumSrc, srcpos, NormFlux
+#ifdef PL
+    use sourceprops, only: NormFluxPL
+#endif
 #ifdef QUASARS
     use sourceprops, only: NormFluxQPL
 #endif
-    type(c_ptr) :: pq
+    type(c_ptr) :: pp, pq
+    pp = c_null_ptr
     pq = c_null_ptr
+#ifdef PL
+    if (NumSrc > 0) pp = loc_dp(NormFluxPL)       ! sourceprops_test.F90:136-162
+#endif
 #ifdef QUASARS
     if (NumSrc > 0) pq = loc_dp(NormFluxQPL)
 #endif
     ! NormFlux is dimensioned (0:NumSrc) in the reference: pass element 1 onwards
     call check(c2ray_b200_set_sources(ctx, int(NumSrc, c_int32_t), int(srcpos, c_int32_t), NormFlux(1:NumSrc), &
-         c_null_ptr, pq), "set_sources")
+         pp, pq), "set_sources")
   end subroutine c2ray_b200_new_sources
 
   !> Drop-in body of evolve3D(time,dt,restart), code/files_for_3D/evolve.F90:78-229.
@@ -326,6 +350,10 @@ contains
     use grid, only: dr, vol
     use cosmology, only: zred
     use material, only: ndens, xh, xhe, temperature_grid, isothermal
+    ! position-dependent clumping and Lyman-limit systems: module variables of material (public by default:
+    ! mat_ini_test.F90:37,45, mat_ini_cubep3m.F90:43,53), refreshed by set_clumping / set_LLS once per redshift slice
+    use material, only: clumping_grid, LLS_grid, coldensh_LLS
+    use c2ray_parameters, only: type_of_clumping, use_LLS, type_of_LLS
     use evolve_data, only: phih_grid, phihe_grid, phiheat, xh_av, xhe_av, xh_intermed, xhe_intermed, photon_loss_all
     use evolve_source, only: sum_nbox_all
     use sizes, only: mesh
@@ -337,11 +365,17 @@ contains
     type(c_ptr) :: pt
 
     call check(c2ray_b200_set_geometry(ctx, dr, vol, zred), "set_geometry")   ! dr, vol, zred change every step
-    ! material's set_clumping / set_LLS run once per redshift slice (C2Ray.F90): when type_of_clumping == 5 or use_LLS
-    ! the host passes the fresh arrays here, e.g.
-    !   call check(c2ray_b200_set_clumping_grid(ctx, loc_sp(clumping_grid)), "set_clumping_grid")
-    !   call check(c2ray_b200_set_LLS(ctx, int(type_of_LLS,c_int32_t), coldensh_LLS, loc_sp(LLS_grid)), "set_LLS")
-    ! (clumping_grid and LLS_grid are private to the material module: it needs two one-line accessor routines)
+    ! evolve_point.F90:484 clumping_point / :177-180 LLS_point: the per-cell values live on the device
+    if (type_of_clumping == 5) then
+       call check(c2ray_b200_set_clumping_grid(ctx, loc_sp(clumping_grid)), "set_clumping_grid")
+    endif
+    if (use_LLS) then
+       if (type_of_LLS == 2) then
+          call check(c2ray_b200_set_LLS(ctx, 2_c_int32_t, 0.0_c_double, loc_sp(LLS_grid)), "set_LLS")
+       else
+          call check(c2ray_b200_set_LLS(ctx, 1_c_int32_t, coldensh_LLS, c_null_ptr), "set_LLS")
+       endif
+    endif
     pt = c_null_ptr
     if (.not.isothermal) pt = loc_sp(temperature_grid)
     call check(c2ray_b200_evolve3d_host(ctx, time, dt, int(restart, c_int32_t), ndens, xh, xhe, pt, st), "evolve3d")

@@ -184,6 +184,18 @@ int c2ray_b200_photoion_rates_batch(c2ray_ctx* ctx, int32_t n, const double* col
  * T3[n][3] = (T_inter, T_avg, T_old) ; nit_out[n] */
 int c2ray_b200_chemistry_batch(c2ray_ctx* ctx, int32_t n, double dt, const double* ndens, double* ion15,
                                const double* phi4, double* T3, int32_t* nit_out);
+/* doric.f90:35 doric(dt,rhe,rhh,ion,phi,yfrac,zfrac,y2afrac,y2bfrac) for n independent states, with the module
+ * coefficients set by ini_rec_colion_factors(T[i]) and material's scalar clumping: rhe[n], ion15[n][15] in/out
+ * (h, he, h_av, he_av overwritten; h_old, he_old read), phi3[n][3] = photo_cell_HI, HeI, HeII, fr4[n][4] = yfrac,
+ * zfrac, y2afrac, y2bfrac (doric.f90:317 prepare_doric_factors). */
+int c2ray_b200_doric_batch(c2ray_ctx* ctx, int32_t n, double dt, const double* rhe, double* ion15, const double* phi3,
+                           const double* fr4, const double* T);
+/* thermal.f90:22 thermal(dt,end_temper,avg_temper,ndens_electron,ndens_atom,ion,phi) for n independent states:
+ * end_temper[n] in/out, avg_temper[n] in/out (left untouched when end_temper <= minitemp, thermal.f90:83), heat[n] =
+ * phi%heat, nsub[n] = explicit sub-steps taken (thermal.f90:98-157). */
+int c2ray_b200_thermal_batch(c2ray_ctx* ctx, int32_t n, double dt, double* end_temper, double* avg_temper,
+                             const double* ndens_electron, const double* ndens_atom, const double* ion15, const double* heat,
+                             int32_t* nsub);
 /* cgsconstants.f90:140 ini_rec_colion_factors: out12 = arech0,brech0,areche0,breche0,oreche0,areche1,breche1,
  * treche1,colli_HI,colli_HeI,colli_HeII,v */
 int c2ray_b200_rec_colion_batch(c2ray_ctx* ctx, int32_t n, const double* T, double* out12);

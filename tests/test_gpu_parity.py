@@ -8,7 +8,8 @@ import pytest
 
 import c2ray_b200
 from oracle import oracle as O
-from common import oracle_setup, oracle_grid, relerr, frac_err, partially_ionized_state
+from common import (oracle_setup, oracle_grid, relerr, frac_err, partially_ionized_state, load_oracle_variant, setup_variant,
+                    FRAC_RTOL, FRAC_ATOL)
 
 pytestmark = pytest.mark.gpu
 synth = c2ray_b200.synth
@@ -51,6 +52,81 @@ def test_photoion_rates_batch(iso, with_qpl):
         # secondary ionisation can change sign)
         err = np.abs(got[:, k] - ref[:, k]) / np.maximum(np.abs(ref[:, k]), 1e-6 * scale[k] + 1e-300)
         assert err.max() < TOL, (k, err.max(), np.argmax(err))
+    c.close()
+
+
+def _random_states(n, seed):
+    rng = np.random.default_rng(seed)
+    x1 = 10.0 ** rng.uniform(-8, -0.001, n); a = 10.0 ** rng.uniform(-8, -0.31, n); b = a * 10.0 ** rng.uniform(-6, -0.1, n)
+    y1 = 10.0 ** rng.uniform(-8, -0.001, n); c1 = 10.0 ** rng.uniform(-8, -0.31, n); d1 = c1 * 10.0 ** rng.uniform(-6, -0.1, n)
+    h = np.stack([1 - x1, x1], 1); he = np.stack([1 - a - b, a, b], 1)
+    old = np.stack([1 - y1, y1, 1 - c1 - d1, c1, d1], 1)
+    return rng, np.concatenate([h, he, h, he, old], axis=1), x1, a, b
+
+
+def _doric_inputs(n, seed):
+    """Physically consistent single-call inputs: config-5 style rates (Gamma_HeI = 0.3 Gamma_HI, Gamma_HeII = 0.01 Gamma_HI,
+    a seventh of the cells without photons), old state = partially ionized, OTS fractions from prepare_doric_factors."""
+    rng, ion15, x1, a, b = _random_states(n, seed)
+    T = 10.0 ** rng.uniform(3.0, 5.0, n)
+    ndens = 10.0 ** rng.uniform(-6, -1, n)
+    dt = 3.0e13
+    g = 10.0 ** rng.uniform(-18, -10, n)
+    g[::7] = 0.0
+    phi3 = np.stack([g, 0.3 * g, 0.01 * g], 1)
+    rhe = ndens * (x1 * (1 - 0.074) + 7.1e-7 + 0.074 * (a + 2 * b))
+    # doric.f90:317-351 prepare_doric_factors on the cell's own columns (path = 1)
+    NH, NHe0, NHe1 = ion15[:, 0] * ndens * (1 - 0.074), ion15[:, 2] * ndens * 0.074, ion15[:, 3] * ndens * 0.074
+    t1, t2 = NH * 1.238e-18, NHe0 * 7.43e-18
+    t3, t4 = NH * 9.907e-22, NHe0 * 1.301e-20
+    t5, t6, t7 = NH * 1.230695924714239e-19, NHe0 * 1.690780687052975e-18, NHe1 * 1.589e-18
+    fr4 = np.stack([t1 / (t1 + t2), t3 / (t3 + t4), t7 / (t7 + t6 + t5), t6 / (t7 + t6 + t5)], 1)
+    return dt, rhe, ndens, ion15, phi3, fr4, T
+
+
+def test_doric_batch():
+    """doric.f90:35-313 alone (SURVEY 8b hook): one call per state against the oracle's doric.  doric forms small
+    fractions as differences of O(1) terms; how far a state amplifies rounding is measured on the oracle's own two builds
+    (with / without FMA contraction) and allowed for, state by state."""
+    p = synth.make_problem(1, n=8)
+    c = c2ray_b200.from_problem(p, tables=oracle_setup(p))
+    V = load_oracle_variant()
+    setup_variant(V, p)
+    n = 3000
+    dt, rhe, ndens, ion15, phi3, fr4, T = _doric_inputs(n, 23)
+    got = c.doric(dt, rhe, ion15, phi3, fr4, T)
+    ref = np.array([O.doric(dt, rhe[i], ndens[i], ion15[i], phi3[i], fr4[i], T[i]) for i in range(n)])
+    alt = np.array([V.doric(dt, rhe[i], ndens[i], ion15[i], phi3[i], fr4[i], T[i]) for i in range(n)])
+    assert np.array_equal(got[:, 10:], ion15[:, 10:])            # h_old, he_old are inputs
+    tol = FRAC_RTOL * np.abs(ref[:, :10]) + FRAC_ATOL
+    noise = np.abs(alt[:, :10] - ref[:, :10]).max(axis=1, keepdims=True)      # the state's own rounding amplification
+    err = np.abs(got[:, :10] - ref[:, :10])
+    assert np.all(err <= tol + 10.0 * noise), float(np.max(err / (tol + 10.0 * noise)))
+    assert np.mean(np.all(err <= tol, axis=1)) > 0.99             # and almost every state needs no allowance at all
+    c.close()
+
+
+def test_thermal_batch():
+    """thermal.f90:22-174 alone (SURVEY 8b hook): end / average temperature and the number of explicit sub-steps."""
+    p = synth.make_problem(1, n=8)
+    c = c2ray_b200.from_problem(p, tables=oracle_setup(p))
+    n = 3000
+    rng, ion15, x1, a, b = _random_states(n, 29)
+    T0 = 10.0 ** rng.uniform(-0.5, 5.5, n)             # includes cells at or below minitemp (avg_temper untouched)
+    ndens = 10.0 ** rng.uniform(-6, 0, n)
+    ne = ndens * (x1 * (1 - 0.074) + 0.074 * (a + 2 * b)) + 1e-12 * ndens
+    heat = 10.0 ** rng.uniform(-32, -22, n) * ndens
+    heat[::5] = 0.0
+    dt = 3.0e13
+    e_g, a_g, ns_g = c.thermal(dt, T0, np.full(n, 123.0), ne, ndens, ion15, heat)
+    ref = [O.thermal(dt, T0[i], ne[i], ndens[i], ion15[i], heat[i]) for i in range(n)]
+    e_o = np.array([r[0] for r in ref]); a_o = np.array([r[1] for r in ref]); ns_o = np.array([r[2] for r in ref])
+    assert np.array_equal(ns_g, ns_o)
+    assert relerr(e_g, e_o) < 1e-9
+    cold = T0 <= 1.0
+    assert np.all(a_g[cold] == 123.0)                  # thermal.f90:83: avg_temper is not touched
+    assert relerr(a_g[~cold], a_o[~cold]) < 1e-9
+    assert ns_o.max() > 50 and cold.any()
     c.close()
 
 
