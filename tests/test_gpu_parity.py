@@ -87,7 +87,8 @@ def _doric_inputs(n, seed):
 def test_doric_batch():
     """doric.f90:35-313 alone (SURVEY 8b hook): one call per state against the oracle's doric.  doric forms small
     fractions as differences of O(1) terms; how far a state amplifies rounding is measured on the oracle's own two builds
-    (with / without FMA contraction) and allowed for, state by state."""
+    (with / without FMA contraction): at least 99.5 % of the states must meet 1e-8 relative + the floor outright, the worst
+    state may be ten times the worst disagreement of the two CPU builds."""
     p = synth.make_problem(1, n=8)
     c = c2ray_b200.from_problem(p, tables=oracle_setup(p))
     V = load_oracle_variant()
@@ -99,10 +100,10 @@ def test_doric_batch():
     alt = np.array([V.doric(dt, rhe[i], ndens[i], ion15[i], phi3[i], fr4[i], T[i]) for i in range(n)])
     assert np.array_equal(got[:, 10:], ion15[:, 10:])            # h_old, he_old are inputs
     tol = FRAC_RTOL * np.abs(ref[:, :10]) + FRAC_ATOL
-    noise = np.abs(alt[:, :10] - ref[:, :10]).max(axis=1, keepdims=True)      # the state's own rounding amplification
-    err = np.abs(got[:, :10] - ref[:, :10])
-    assert np.all(err <= tol + 10.0 * noise), float(np.max(err / (tol + 10.0 * noise)))
-    assert np.mean(np.all(err <= tol, axis=1)) > 0.99             # and almost every state needs no allowance at all
+    err = np.abs(got[:, :10] - ref[:, :10]) / tol
+    noise = float((np.abs(alt[:, :10] - ref[:, :10]) / tol).max())     # worst state of the two CPU builds, in units of tol
+    assert np.mean(np.all(err <= 1.0, axis=1)) > 0.995                  # nearly every state: 1e-8 relative + the floor
+    assert err.max() <= max(1.0, 10.0 * noise), (float(err.max()), noise)
     c.close()
 
 
