@@ -147,6 +147,9 @@ struct c2ray_ctx {
   BandRec h_band[NumFreqBnd];  // host copy of the band records in constant memory
   int n_sm = 148;          // multiprocessors of this context's device
   int chemq_per_sm = 0;    // resident CTAs per SM of k_global_pass_q (queried once per context)
+  int chem_thermal_min = 0;     // env C2RAY_CHEM_TMIN: lanes that must wait in THERMAL before the queue kernel runs a burst (0: any)
+  int chem_burst = CHEM_BURST;  // env C2RAY_CHEM_BURST: thermal sub-steps per turn of the queue kernel's state machine
+  double last_nit_per_cell = 0.0;  // do_chemistry iterations per cell of the previous global pass
   int chem_mode = -1;      // -1 auto, 0 one cell per thread, 1 queue-driven (env C2RAY_CHEM_QUEUE overrides)
   double last_nsub_per_cell = 0.0;  // thermal sub-steps per cell of the previous global pass
   int* d_nit = nullptr;
@@ -157,6 +160,7 @@ struct c2ray_ctx {
   int* d_nbox_all = nullptr;   // sub-box count per source of the last pass (this rank's sources; summed over ranks)
   std::vector<int> my_ids;     // 0-based ids of this rank's sources
   std::vector<char> src_pl, src_qpl;  // per source: NormFluxPL > 0, NormFluxQPL > 0
+  std::vector<double> src_flux;       // per source: total photon rate (evolve_source.F90:122-128), the balanced schedule's first cost model
   int* d_srcids_run = nullptr; // this rank's sources ordered for the sweep: black-body-only sources first
   int n_single = 0;            // how many of them take the single-SED kernel
   int run_key = -1;            // what d_srcids_run was built for (table presence bits); -1: rebuild
@@ -315,9 +319,23 @@ int upload_my_sources(c2ray_ctx* c) {
   return 0;
 }
 
+void balanced_partition(int NumSrc, const long long* cost, int npr, int* owner);
+
 int rebuild_my_sources(c2ray_ctx* c) {
   c->my_ids.clear();
-  for (int ns1 = 1 + c->rank; ns1 <= c->NumSrc; ns1 += c->npr) c->my_ids.push_back(ns1 - 1);  // master_slave.F90:85
+  if (c->schedule == 1 && c->npr > 1 && (int)c->src_flux.size() == c->NumSrc && c->NumSrc > 0) {
+    // Balanced schedule before any pass has left cost records: deal by photon rate, brightest first to the least loaded
+    // rank (how far a source traces grows with its flux; the records of the first pass replace this guess).
+    double fmax = 0.0;
+    for (double f : c->src_flux) fmax = std::max(fmax, f);
+    std::vector<long long> cost(c->NumSrc);
+    for (int i = 0; i < c->NumSrc; i++) cost[i] = fmax > 0.0 ? (long long)(1.0e9 * c->src_flux[i] / fmax) + 1 : 1;
+    std::vector<int> owner(c->NumSrc);
+    balanced_partition(c->NumSrc, cost.data(), c->npr, owner.data());
+    for (int i = 0; i < c->NumSrc; i++) if (owner[i] == c->rank) c->my_ids.push_back(i);
+  } else {
+    for (int ns1 = 1 + c->rank; ns1 <= c->NumSrc; ns1 += c->npr) c->my_ids.push_back(ns1 - 1);  // master_slave.F90:85
+  }
   if (c->d_nbox_all) { cudaFree(c->d_nbox_all); c->d_nbox_all = nullptr; }
   if (c->NumSrc > 0) {
     CK(cudaMalloc(&c->d_nbox_all, sizeof(int) * c->NumSrc));
@@ -775,7 +793,10 @@ int global_pass_launch(c2ray_ctx* c, double dt, int* d_nit, size_t p_begin = 0, 
   ChemPtrs P{c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->temp, c->rates, c->N3, c->d_clump};
   // auto: the queue-driven kernel pays off once cells need many thermal sub-steps (divergence); measured break-even
   // between 10 and 40 sub-steps per cell (config 2: ~10, simple kernel faster; config 5: 42, queue 2x faster)
-  const bool use_queue = c->chem_mode == 1 || (c->chem_mode < 0 && c->last_nsub_per_cell > 20.0);
+  // (isothermal passes have no sub-steps: there the queue pays once cells iterate, 4.78 -> 5.60 G cells/s on the config-5
+  // inputs -- profiles/r2_ab4_chem.log)
+  const bool use_queue = c->chem_mode == 1 || (c->chem_mode < 0 && (c->last_nsub_per_cell > 20.0 ||
+                                                                      (c->par.isothermal && c->last_nit_per_cell > 1.5)));
   if (use_queue) {
     // queue-driven: a persistent grid of lanes drawing cells from a counter (k_global_pass_q)
     CK(cudaMemsetAsync(c->d_next_cell, 0, sizeof(unsigned long long), c->stream));
@@ -784,7 +805,7 @@ int global_pass_launch(c2ray_ctx* c, double dt, int* d_nit, size_t p_begin = 0, 
       c->chemq_per_sm = std::max(c->chemq_per_sm, 1);
     }
     const unsigned blocks = (unsigned)std::min<size_t>((ncell + 127) / 128, (size_t)c->n_sm * c->chemq_per_sm);
-    LAUNCH(c, k_global_pass_q, blocks, 128, P, dt, c->d_chem, d_nit, c->d_next_cell, p_begin, p_end);
+    LAUNCH(c, k_global_pass_q, blocks, 128, P, dt, c->d_chem, d_nit, c->d_next_cell, p_begin, p_end, c->chem_burst, c->chem_thermal_min);
   } else {
     const unsigned blocks = (unsigned)((ncell + 127) / 128);
     LAUNCH(c, k_global_pass, blocks, 128, P, dt, c->d_chem, d_nit, p_begin, p_end);
@@ -894,6 +915,8 @@ static int init_device_state(c2ray_ctx* c) {
   CK(cudaMalloc(&c->d_chemred, 6 * sizeof(double)));
   if (const char* e = getenv("C2RAY_SPLIT_CHEM")) c->split_chem = atoi(e);
   if (const char* e = getenv("C2RAY_CHEM_QUEUE")) c->chem_mode = atoi(e);
+  if (const char* e = getenv("C2RAY_CHEM_BURST")) c->chem_burst = std::max(1, atoi(e));
+  if (const char* e = getenv("C2RAY_CHEM_TMIN")) c->chem_thermal_min = std::min(32, std::max(0, atoi(e)));
   CK(cudaMalloc(&c->d_cool, 5 * TEMPPOINTS * sizeof(double)));
   CK(cudaMalloc(&c->d_tb, sizeof(TableBuild)));
   int rc = upload_band_const(c);
@@ -1129,7 +1152,9 @@ int c2ray_b200_set_sources(c2ray_ctx* c, int32_t NumSrc, const int32_t* srcpos, 
   c->sum_nf[0] = c->sum_nf[1] = c->sum_nf[2] = 0.0;
   c->last_pass_updates = -1;
   c->src_pl.assign(NumSrc, 0); c->src_qpl.assign(NumSrc, 0);
+  c->src_flux.assign(NumSrc, 0.0);
   for (int i = 0; i < NumSrc; i++) {
+    c->src_flux[i] = nf[i] * c->S_star[0] + (nfpl ? nfpl[i] * c->S_star[1] : 0.0) + (nfqpl ? nfqpl[i] * c->S_star[2] : 0.0);
     c->sum_nf[0] += nf[i];
     if (nfpl) { c->sum_nf[1] += nfpl[i]; c->src_pl[i] = nfpl[i] > 0.0; }
     if (nfqpl) { c->sum_nf[2] += nfqpl[i]; c->src_qpl[i] = nfqpl[i] > 0.0; }
@@ -1340,6 +1365,7 @@ int c2ray_b200_global_pass(c2ray_ctx* c, double dt, int32_t* conv_flag, int32_t*
   if (nit_out) CK(cudaMemcpyAsync(nit_out, c->d_nit, c->N3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->last_nsub_per_cell = (double)t.nsub_total / (double)c->N3;
+  c->last_nit_per_cell = (double)t.nit_total / (double)c->N3;
   if (conv_flag) *conv_flag = t.conv_flag;
   return C2RAY_OK;
 }
@@ -1399,6 +1425,7 @@ int c2ray_b200_evolve3d(c2ray_ctx* c, double /*time*/, double dt, int32_t restar
     CK(cudaStreamSynchronize(c->stream));
     conv_flag = cht.conv_flag;
     c->last_nsub_per_cell = (double)cht.nsub_total / (double)c->N3;
+    c->last_nit_per_cell = (double)cht.nit_total / (double)c->N3;
     S.chem_cells += (int64_t)chunk;
   }
   for (;;) {
@@ -1448,6 +1475,7 @@ int c2ray_b200_evolve3d(c2ray_ctx* c, double /*time*/, double dt, int32_t restar
     CK(cudaStreamSynchronize(c->stream));
     conv_flag = cht.conv_flag;
     c->last_nsub_per_cell = (double)cht.nsub_total / (double)c->N3;
+    c->last_nit_per_cell = (double)cht.nit_total / (double)c->N3;
     if (niter <= C2RAY_MAX_ITER_HIST) S.conv_hist[niter - 1] = conv_flag;
     S.rt_updates += (int64_t)swt.updates;
     if (c->NumSrc > 0) c->last_pass_updates = (long long)swt.updates;
@@ -1725,7 +1753,7 @@ int c2ray_b200_set_source_schedule(c2ray_ctx* c, int32_t mode) {
   if (!c || mode < 0 || mode > 1) return fail(C2RAY_ERR_ARG, "schedule must be 0 (static round robin) or 1 (balanced)");
   c->schedule = mode;
   CK(cudaSetDevice(c->device));
-  return rebuild_my_sources(c);  // both schedules start from the round-robin deal
+  return rebuild_my_sources(c);  // static: round robin; balanced: dealt by photon rate until a pass has left cost records
 }
 
 int c2ray_b200_balanced_partition(int32_t NumSrc, const int64_t* cost, int32_t npr, int32_t* owner) {
@@ -1808,6 +1836,7 @@ int c2ray_b200_bench_global_pass(c2ray_ctx* c, double dt, int32_t reps, double* 
     CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
     total += ms;
     c->last_nsub_per_cell = (double)t.nsub_total / (double)c->N3;
+    c->last_nit_per_cell = (double)t.nit_total / (double)c->N3;
   }
   if (ms_per_pass) *ms_per_pass = total / reps;
   if (conv_flag) *conv_flag = t.conv_flag;

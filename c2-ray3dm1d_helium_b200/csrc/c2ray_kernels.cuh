@@ -518,11 +518,13 @@ k_global_pass(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out,
 // TEST (convergence; store or loop) -- and a lane that finishes its cell immediately draws the next cell index from a
 // global counter (one atomic per warp refill).  The arithmetic per cell is exactly that of do_chemistry.
 // ------------------------------------------------------------------------------------------------
-constexpr int CHEM_BURST = 32;  // thermal sub-steps per state-machine turn (8: 36 ms, 32: 30 ms on config 5 at 256^3)
+constexpr int CHEM_BURST = 32;  // default thermal sub-steps per state-machine turn (8: 36 ms, 32: 30 ms on config 5 at 256^3)
+// (holding lanes back until a dozen of them wait for IONIZE, so that block runs better filled: no change, 28.2-28.5 ms at
+// any threshold -- profiles/r2_ab4_chem.log)
 
 __global__ void __launch_bounds__(128, 4)
 k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_out, unsigned long long* next_cell,
-                size_t p_begin, size_t p_end) {
+                size_t p_begin, size_t p_end, int burst, int thermal_min) {
   const size_t N3 = P.N3;
   const bool iso = d_run.isothermal != 0;
   const unsigned lane = threadIdx.x & 31;
@@ -577,6 +579,12 @@ k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_ou
     }
     if (__all_sync(0xffffffffu, phase == IDLE)) break;  // every lane idle and the queue empty
 
+    // thermal_min > 0 holds the THERMAL burst back until that many lanes wait in it (or nothing else is left to do this
+    // turn), so that cheap cells stream through the other lanes while expensive ones gather.  Measured: no effect at any
+    // threshold (profiles/r2_ab5_chem_thermal_batching.log), default 0.  What does matter is the warp-wide vote below:
+    // it makes the lanes that left the divergent IONIZE block reconverge BEFORE the burst, so the sub-step loop runs once
+    // for the warp instead of once per diverged group (config-5 thermal pass at 256^3: 28.4 -> 20.7 ms).
+    const bool others_busy = __any_sync(0xffffffffu, phase == IONIZE);
     // ---- IONIZE: one do_chemistry iteration up to the thermal call (evolve_point.F90:488-600) ---------------------
     if (phase == IONIZE) {
       nit++;
@@ -591,10 +599,11 @@ k_global_pass_q(ChemPtrs P, double dt, ChemTotals* tot, int* __restrict__ nit_ou
       }
     }
     // ---- THERMAL: a burst of explicit sub-steps (thermal.f90:98-157) -----------------------------------------------
-    if (phase == THERMAL) {
+    const int n_thermal = __popc(__ballot_sync(0xffffffffu, phase == THERMAL));
+    if (phase == THERMAL && (n_thermal >= thermal_min || !others_busy)) {
       bool done = false;
 #pragma unroll 1
-      for (int k = 0; k < CHEM_BURST && !done; k++) { done = thermal_substep(TS, dt, de, n, ion, heat); nsub++; }
+      for (int k = 0; k < burst && !done; k++) { done = thermal_substep(TS, dt, de, n, ion, heat); nsub++; }
       if (done) phase = TEST;
     }
     // ---- TEST: finish thermal, convergence test, store (evolve_point.F90:607-644, :397-435) --------------------------
