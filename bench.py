@@ -271,15 +271,18 @@ def run_b200(args):
     h_ndens, h_xh0, h_xhe0, h_T0 = pin(p["ndens"]), pin(p["xh"]), pin(p["xhe"]), pin(p["temperature_grid"])
     h_xh, h_xhe, h_T = torch.empty_like(h_xh0).pin_memory(), torch.empty_like(h_xhe0).pin_memory(), torch.empty_like(h_T0).pin_memory()
     e2e_steps = max(1, min(args.steps, 2))
-    barrier()
-    t0 = time.perf_counter()
-    upd_e2e = 0
+    upd_e2e, t_e2e = 0, 0.0
     for step in range(e2e_steps):
+        # the call updates xh, xhe, temperature_grid in place: put the start state back first (host-to-host copies of the
+        # bench's own scaffolding, outside the timed region), then time the call itself -- H2D of the inputs from pinned
+        # host memory, the whole time step, D2H of the results
         h_xh.copy_(h_xh0); h_xhe.copy_(h_xhe0); h_T.copy_(h_T0)
+        barrier()
+        t0 = time.perf_counter()
         s = c.evolve3D_host(0.0, p["dt"], 0, h_ndens.numpy(), h_xh.numpy(), h_xhe.numpy(), h_T.numpy())
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
         upd_e2e += s["rt_updates"]
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
     h2d = N3 * (8 + 16 + 24 + 12)
     d2h = N3 * (16 + 24 + 12)
 

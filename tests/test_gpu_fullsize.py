@@ -66,7 +66,7 @@ def compare_fields(rec, names, got, ref, alt, iso):
             e, nz = rel_err(a.astype(np.float64), b.astype(np.float64))
             e_cpu = float(rel_err(c.astype(np.float64), b.astype(np.float64))[0].max())
             rec[name] = {"max_rel": float(e.max()), "cells_differing": int((e > 0).sum()), "oracle_fma_vs_oracle_max_rel": e_cpu,
-                         "bound": max(1.3e-7, NOISE_FACTOR * e_cpu)}
+                         "bound": 1.3e-7 if e_cpu <= 1.3e-7 else NOISE_FACTOR * e_cpu}   # one float ulp unless the CPU builds differ by more
             if not rec[name]["max_rel"] < rec[name]["bound"]:
                 failed.append(name)
             continue

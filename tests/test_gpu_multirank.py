@@ -53,7 +53,7 @@ def test_nccl_path_against_single_rank_and_oracle(world):
             f.write(out)
     except OSError:
         pass
-    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("rank ")]
-    print("\n".join(lines))
+    print("\n".join(ln for ln in r.stdout.splitlines() if "rank " in ln))
     assert r.returncode == 0, out[-4000:]
-    assert len(lines) == world and all(ln.rstrip().endswith("-> OK") for ln in lines), out[-4000:]
+    # (the ranks' lines can run into each other on the shared stdout: count verdicts, not lines)
+    assert r.stdout.count("-> OK") == world and "MISMATCH" not in r.stdout, out[-4000:]
