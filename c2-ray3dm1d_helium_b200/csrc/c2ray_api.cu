@@ -135,8 +135,11 @@ struct c2ray_ctx {
   double sweep_lanes_fill = 1.0;            // env C2RAY_SWEEP_LANES_FILL: resident waves the split threads may fill
   int sparse_records = 1;                   // env C2RAY_SPARSE_RECORDS: per-level cell records when the sources cover little of the mesh
   long long last_pass_updates = -1;         // updates of this rank's previous pass (-1: none yet)
+  int dead_bands = 1;                       // env C2RAY_DEAD_BANDS: skip bands whose table rows are all zero from tau_in on (c2ray_photo.cuh)
   int sweep_pdl = 1;                        // env C2RAY_SWEEP_PDL: programmatic dependent launch between the shells of a level
   double* d_scratch = nullptr;
+  double* d_lossbuf = nullptr;              // deterministic mode only
+  int lossbuf_cap = 0;
   int slots_cap = 0;
   bool slots_budget_limited = false;
   SweepGeom geom{};
@@ -450,6 +453,17 @@ int sweep_all(c2ray_ctx* c) {
       LAUNCH(c, k_cell_records, (unsigned)((c->N3 + 255) / 256), 256, c->ndens, c->xh_av, c->xhe_av, c->N3,
              c->par.isothermal ? 1 : 0, c->d_cellrec);
     GridPtrs G{c->d_cellrec, c->rates, c->N3, c->lls_type, c->coldensh_LLS, c->d_lls};
+    double* lossbuf = nullptr;   // deterministic mode: per-cell photon-loss contributions of the current shell (k_loss_sum)
+    if (c->par.deterministic) {
+      if (c->lossbuf_cap < g.cap) {
+        if (c->d_lossbuf) cudaFree(c->d_lossbuf);
+        c->d_lossbuf = nullptr;
+        CK(cudaMalloc(&c->d_lossbuf, sizeof(double) * (size_t)g.cap));
+        CK(cudaMemset(c->d_lossbuf, 0, sizeof(double) * (size_t)g.cap));
+        c->lossbuf_cap = g.cap;
+      }
+      lossbuf = c->d_lossbuf;
+    }
     ngroups = c->par.deterministic ? 1 : std::max(1, std::min(c->sweep_groups, std::min(c->slots_cap, c->n_mine)));
     const int region = c->par.deterministic ? 1 : c->slots_cap / ngroups;  // slots per stream group
     const int batch = region * ngroups;                                     // sources in flight at a time
@@ -559,7 +573,7 @@ int sweep_all(c2ray_ctx* c) {
   do {                                                                                                                        \
     CK(launch_overlapped(k_sweep_shell<ISO, MULTI, LANES>, (unsigned)blocks, 128u, c->gstream[q], pdl, c->d_slots + goff[q],  \
                          (const int*)(c->d_active + goff[q]), c->d_gtot + q, g, G,                                            \
-                         c->d_scratch + (size_t)goff[q] * slot_stride, r));                                                   \
+                         c->d_scratch + (size_t)goff[q] * slot_stride, r, lossbuf));                                          \
     c->launches++; c->sweep_launches++;                                                                                        \
   } while (0)
 #define SWEEP2(ISO, MULTI)                         \
@@ -576,6 +590,8 @@ int sweep_all(c2ray_ctx* c) {
             else { if (c->par.isothermal) SWEEP2(true, false); else SWEEP2(false, false); }
 #undef SWEEP2
 #undef SWEEP
+            if (lossbuf)  // deterministic mode: one source, its slot is the first of the group
+              LAUNCH_S(c, c->gstream[q], k_loss_sum, 1, 1024, c->d_slots + goff[q], lossbuf, (int)(r == 0 ? 1 : 24LL * r * r + 2));
           }
         }
         if ((long long)g.subboxsize * b >= reach3) break;  // the do-while's extent test fails for every source
@@ -905,6 +921,7 @@ static int init_device_state(c2ray_ctx* c) {
   for (auto& ev : c->ev_join) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   if (const char* e = getenv("C2RAY_SWEEP_SPLIT")) c->sweep_split = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_PDL")) c->sweep_pdl = atoi(e);
+  if (const char* e = getenv("C2RAY_DEAD_BANDS")) c->dead_bands = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_LANES_MODE")) c->sweep_lanes_mode = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_LANES_FILL")) c->sweep_lanes_fill = std::max(0.1, atof(e));
   if (const char* e = getenv("C2RAY_SPARSE_RECORDS")) c->sparse_records = atoi(e);
@@ -932,7 +949,7 @@ int c2ray_b200_destroy(c2ray_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   void* ptrs[] = {c->ndens, c->xh, c->xhe, c->xh_av, c->xhe_av, c->xh_int, c->xhe_int, c->rates, c->temp, c->snap_xh,
                   c->snap_xhe, c->snap_temp, c->d_srcpos, c->d_nf, c->d_nfpl, c->d_nfqpl, c->d_tb, c->d_cool,
-                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_cellrec, c->d_next_cell, c->d_chemred, c->d_clump, c->d_lls, c->d_nbox_all, c->d_srcids_run};
+                  c->d_slots, c->d_active, c->d_tot, c->d_gtot, c->d_scratch, c->d_chem, c->d_sums, c->d_nit, c->d_cellrec, c->d_next_cell, c->d_chemred, c->d_clump, c->d_lls, c->d_nbox_all, c->d_srcids_run, c->d_lossbuf};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int s = 0; s < 3; s++) for (int k = 0; k < 4; k++) if (c->tab[s][k]) cudaFree(c->tab[s][k]);
   for (int s = 0; s < 3; s++) if (c->packed[s]) cudaFree(c->packed[s]);
@@ -988,6 +1005,8 @@ static int pack_tables(c2ray_ctx* c, int s) {
   CK(cudaMemcpyAsync(dead, d_tmp, sizeof(dead), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaFree(d_tmp));
+  if (!c->dead_bands)  // env C2RAY_DEAD_BANDS=0: no band is ever skipped (the bit-identity test's reference run)
+    for (double& v : dead) v = INFINITY;
   CK(cudaMemcpyToSymbol(d_dead, dead, sizeof(dead), (size_t)s * sizeof(dead)));
   if (s == 0) {
     for (int q = 0; q < NumFreqBnd; q++) c->h_band[q].dead_bb = dead[q];

@@ -226,7 +226,10 @@ __global__ void k_cell_records_level(const Slot* __restrict__ slots, const int* 
 template <bool ISO, bool MULTI, int LANES>
 __global__ void __launch_bounds__(128, MULTI ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS)
 k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot, SweepGeom g,
-              GridPtrs G, double* __restrict__ scratch, int r) {
+              GridPtrs G, double* __restrict__ scratch, int r, double* __restrict__ lossbuf) {
+  // lossbuf != nullptr (deterministic mode, one source at a time): every cell of the shell writes its photon-loss
+  // contribution (0 for cells off the sub-box boundary or outside the box) and k_loss_sum adds them in a fixed order,
+  // instead of atomic adds whose order varies from run to run
   // Programmatic dependent launch: within a sub-box level the next shell's launch is allowed to start filling SMs
   // while this one drains (its threads decode their cell, test the box and fetch the cell record, then wait below
   // before they touch the shell scratch).  Without the launch attribute both instructions are no-ops.
@@ -254,7 +257,10 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     Slot& S = slots[sid];
     int di, dj, dk;
     shell_decode(c, r, di, dj, dk);
-    if (di < -S.lo[0] || di > S.hi[0] || dj < -S.lo[1] || dj > S.hi[1] || dk < -S.lo[2] || dk > S.hi[2]) continue;
+    if (di < -S.lo[0] || di > S.hi[0] || dj < -S.lo[1] || dj > S.hi[1] || dk < -S.lo[2] || dk > S.hi[2]) {
+      if (lossbuf && lane_j == 0) lossbuf[c] = 0.0;
+      continue;
+    }
     double* cur = scratch + sid * slot_stride + (size_t)par * 3 * g.cap;
     const double* prev = scratch + sid * slot_stride + (size_t)(par ^ 1) * 3 * g.cap;
 
@@ -396,6 +402,11 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     // one of a handful of sources: a full warp working on one source sums its contributions by shuffles first, so the
     // per-source counter sees one atomic per warp instead of 32.
     const bool is_loss = di == -S.lo[0] || dj == -S.lo[1] || dk == -S.lo[2] || di == S.hi[0] || dj == S.hi[1] || dk == S.hi[2];
+    if (lossbuf) {
+      lossbuf[c] = is_loss ? fdiv(phi.photo_out * d_run.vol, vol_ph) : 0.0;
+      done++;
+      continue;
+    }
     const unsigned am = __activemask();
     if (__any_sync(am, is_loss)) {
       double lv = is_loss ? fdiv(phi.photo_out * d_run.vol, vol_ph) : 0.0;
@@ -414,6 +425,21 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
   __syncwarp();
   done = __reduce_add_sync(0xffffffffu, done);
   if ((threadIdx.x & 31) == 0 && done) atomicAdd(&tot->updates, (unsigned long long)done);
+}
+
+// Deterministic mode: photon_loss_src += sum of the shell's per-cell contributions, in an order that depends on
+// nothing but the shell size (thread t adds cells t, t+1024, ... in sequence; then a fixed tree over the 1024 partial sums).
+__global__ void __launch_bounds__(1024) k_loss_sum(Slot* slot, const double* __restrict__ lossbuf, int ncell) {
+  __shared__ double sh[1024];
+  double v = 0.0;
+  for (int c = threadIdx.x; c < ncell; c += 1024) v += lossbuf[c];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) slot->loss += sh[0];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -67,6 +67,35 @@ def test_deterministic_mode_is_reproducible():
         assert np.array_equal(a, b)  # one source at a time in source order: no atomic reordering
 
 
+def test_deterministic_mode_photon_loss_is_bitwise_reproducible():
+    """In deterministic mode the photon loss over a sub-box boundary (evolve_point.F90:310-314, the quantity the `do while`
+    of evolve_source.F90:136 tests) is summed in a fixed order (k_loss_sum), not by atomic adds: loss and sub-box count of
+    every source are bit for bit the same from run to run, and the loss agrees with the oracle's to rounding."""
+    p = synth.make_problem(3, n=24, num_src=4)
+    p["subboxsize"] = 4
+    p["NormFlux"] = p["NormFlux"] * 50.0      # bright enough for several sub-box levels
+    tables = oracle_setup(p)
+    g = oracle_grid(p)
+    xh, xhe = partially_ionized_state(p, seed=5)
+    runs = []
+    for rep in range(3):
+        c = c2ray_b200.from_problem(p, tables=tables, deterministic=True)
+        c.begin_step(); c.set_work_state(xh, xhe, xh, xhe); c.set_rates_to_zero()
+        runs.append([c.do_source(p["dt"], ns, 1) for ns in range(1, 5)])
+        c.close()
+    assert runs[0] == runs[1] == runs[2]
+    assert max(nb for nb, _ in runs[0]) >= 2
+    # oracle: one source at a time
+    for ns in range(1, 5):
+        q = dict(p); q["srcpos"] = p["srcpos"][ns - 1:ns]; q["NormFlux"] = p["NormFlux"][ns - 1:ns]
+        q["NormFluxQPL"] = p["NormFluxQPL"][ns - 1:ns]
+        go = oracle_grid(q)
+        go.set_work_state(xh, xhe, xh, xhe); go.set_rates_to_zero()
+        upd, nbox, loss, snb = go.pass_all_sources()
+        assert runs[0][ns - 1][0] == int(nbox[0])
+        assert abs(runs[0][ns - 1][1] - loss) <= 1e-10 * abs(loss) + 1e-300
+
+
 @pytest.mark.parametrize("mode", ["0", "1"])
 def test_both_global_pass_kernels(mode, monkeypatch):
     """C2RAY_CHEM_QUEUE=0: one cell per thread; =1: queue-driven lanes.  Same arithmetic, same integers."""
@@ -341,3 +370,30 @@ def test_failed_init_releases_the_device():
     c = c2ray_b200.from_problem(p)
     assert c.evolve3D(0.0, p["dt"], 0)["niter"] >= 2
     c.close()
+
+
+def test_dead_band_skip_is_bit_identical(monkeypatch):
+    """A band whose table rows are all exactly zero from tau_in on is skipped (c2ray_photo.cuh, d_dead): the rate grids,
+    the photon loss and the sub-box counts must come out bit for bit as without the skip.  A thick box (optical depth
+    ~70 per neutral cell at the hydrogen edge, configs[2] style with BB + QPL sources) so that bands do die; deterministic
+    mode so that the order of the atomic adds is fixed."""
+    p = synth.make_problem(3, n=48, num_src=3)
+    # (synth scales the box with the mesh: the cells are as thick as those of the 256^3 configuration)
+    p["NormFluxQPL"] = np.ascontiguousarray(0.1 * p["NormFlux"] * p["S_star"] / p["qpl"]["S_star"])
+    out = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("C2RAY_DEAD_BANDS", flag)
+        c = c2ray_b200.from_problem(p, deterministic=True)
+        c.begin_step()
+        res = []
+        for it in range(2):
+            c.set_rates_to_zero()
+            upd = c.pass_all_sources(it + 1, p["dt"])
+            res.append((upd,) + tuple(a.copy() for a in c.get_rates()))
+            c.global_pass(p["dt"])
+        out.append(res)
+        c.close()
+    for a, b in zip(*out):
+        assert a[0] == b[0]
+        for x, y in zip(a[1:], b[1:]):
+            assert np.array_equal(x, y)
