@@ -136,8 +136,6 @@ struct c2ray_ctx {
   int sparse_records = 1;                   // env C2RAY_SPARSE_RECORDS: per-level cell records when the sources cover little of the mesh
   long long last_pass_updates = -1;         // updates of this rank's previous pass (-1: none yet)
   int dead_bands = 1;                       // env C2RAY_DEAD_BANDS: skip bands whose table rows are all zero from tau_in on (c2ray_photo.cuh)
-  int sweep_speculate = 1;                  // env C2RAY_SWEEP_SPECULATE: few sources: enqueue the levels the previous pass reached without a host wait
-  int prev_levels = 0;                      // sub-box levels the previous pass of this context needed (minus one: that level asks)
   int sweep_pdl = 1;                        // env C2RAY_SWEEP_PDL: programmatic dependent launch between the shells of a level
   double* d_scratch = nullptr;
   double* d_lossbuf = nullptr;              // deterministic mode only
@@ -519,16 +517,13 @@ int sweep_all(c2ray_ctx* c) {
       const int reach3 = std::min(g.R[2], g.L[2]);
       int nact[MAX_SWEEP_GROUPS];
       for (int q = 0; q < ngroups; q++) nact[q] = gns[q];
-      int levels_used = 0;
       for (int b = 1;; b++) {
         for (int q = 0; q < ngroups; q++)
           if (nact[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q], c->d_nbox_all);
-        // With a handful of sources the host wait per level is a tenth of the pass (one source at 128^3: six waits of
-        // ~15 us in 1.1 ms), and how many levels the sources need changes slowly from one global iteration to the next:
-        // levels the previous pass reached are enqueued without asking (the kernels read the active count on the device;
-        // a level nobody traces any more costs ten empty launches), the first level beyond them asks again.
-        const bool speculate = c->sweep_speculate && !sparse_records && c->n_mine <= 4 && b <= c->prev_levels;
-        if (b > 1 && !speculate) {
+        // (enqueueing the levels the previous pass reached without this wait was tried for the few-source case: no change,
+        // 53.2 ms of sweeps per step for one source at 128^3 either way -- the wait overlaps the draining level;
+        // profiles/r2_ab8_speculate.log)
+        if (b > 1) {
           // From the second sub-box on most sources have dropped out (photon loss below 1e-10 of the flux): fetch the
           // number still active so that the shells of a level nobody traces are not launched at all and the grids
           // of the others are sized to the work that exists.  One short host wait per sub-box level.
@@ -602,14 +597,10 @@ int sweep_all(c2ray_ctx* c) {
               LAUNCH_S(c, c->gstream[q], k_loss_sum, 1, 1024, c->d_slots + goff[q], lossbuf, (int)(r == 0 ? 1 : 24LL * r * r + 2));
           }
         }
-        levels_used = b;
         if ((long long)g.subboxsize * b >= reach3) break;  // the do-while's extent test fails for every source
       }
       for (int q = 0; q < ngroups; q++)  // close the sources still active
         if (nact[q] > 0) LAUNCH_S(c, c->gstream[q], k_decide, 1, 256, c->d_slots + goff[q], gns[q], g, c->d_gtot + q, c->d_active + goff[q], c->d_nbox_all);
-      // levels whose active count was fetched and found non-zero, plus the speculated ones: an upper bound of what the
-      // sources needed, re-learned downwards by the fetch that follows the last speculated level of the next pass
-      c->prev_levels = levels_used - 1;
     }
     for (int q = 0; q < ngroups; q++) {
       CK(cudaEventRecord(c->ev_join[q], c->gstream[q]));
@@ -933,7 +924,6 @@ static int init_device_state(c2ray_ctx* c) {
   for (auto& ev : c->ev_join) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   if (const char* e = getenv("C2RAY_SWEEP_SPLIT")) c->sweep_split = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_PDL")) c->sweep_pdl = atoi(e);
-  if (const char* e = getenv("C2RAY_SWEEP_SPECULATE")) c->sweep_speculate = atoi(e);
   if (const char* e = getenv("C2RAY_DEAD_BANDS")) c->dead_bands = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_LANES_MODE")) c->sweep_lanes_mode = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_LANES_FILL")) c->sweep_lanes_fill = std::max(0.1, atof(e));
@@ -1183,7 +1173,6 @@ int c2ray_b200_set_sources(c2ray_ctx* c, int32_t NumSrc, const int32_t* srcpos, 
   c->have_pl_flux = nfpl != nullptr; c->have_qpl_flux = nfqpl != nullptr;
   c->sum_nf[0] = c->sum_nf[1] = c->sum_nf[2] = 0.0;
   c->last_pass_updates = -1;
-  c->prev_levels = 0;
   c->src_pl.assign(NumSrc, 0); c->src_qpl.assign(NumSrc, 0);
   c->src_flux.assign(NumSrc, 0.0);
   for (int i = 0; i < NumSrc; i++) {

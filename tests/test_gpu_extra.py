@@ -8,7 +8,8 @@ import pytest
 import c2ray_b200
 from c2ray_b200 import capi
 from oracle import oracle as O
-from common import oracle_setup, oracle_grid, relerr, frac_err, partially_ionized_state
+from common import (oracle_setup, oracle_grid, relerr, frac_err, partially_ionized_state, load_oracle_variant, setup_variant,
+                    calibrated_compare, COMPLEMENT_ULPS)
 
 pytestmark = pytest.mark.gpu
 synth = c2ray_b200.synth
@@ -206,10 +207,23 @@ def test_all_three_seds():
     assert sg["niter"] == so["niter"] and list(sg["conv_hist"]) == list(so["conv_hist"]) and sg["rt_updates"] == so["rt_updates"]
     # In this hard-spectrum case a handful of cells run do_chemistry to its 401-iteration limit without converging (in the
     # oracle too: tools/diag_evolve.py), i.e. they sit on a limit cycle that amplifies last-digit differences during the
-    # intermediate global iterations (up to 1e-4); the converged end state still agrees to a few 1e-10.
-    assert frac_err(xh, xh_o) < 5 and frac_err(xhe, xhe_o) < 5 and relerr(T, T_o) < 1e-6
-    for a, b in zip(c.get_rates(), g.get_rates()):
-        assert relerr(a, b, 1e-6 * np.abs(b).max() + 1e-300) < 1e-5  # rate grids of the last iteration: computed from the second-to-last, not yet settled, state
+    # intermediate global iterations.  How far is measured on the reference's own two CPU builds and allowed for, decade by
+    # decade of the value (tests/common.py calibrated_compare; pure relative 1e-8 where the two CPU builds agree).
+    gv = setup_variant(load_oracle_variant(), p)
+    sv = gv.evolve3d(p["dt"])
+    assert sv["niter"] == so["niter"]
+    xh_v, xhe_v, T_v = gv.get_state()
+    for name, a, b, v in (("xh", xh, xh_o, xh_v), ("xhe", xhe, xhe_o, xhe_v)):
+        for comp in range(a.shape[0]):
+            rec, ok = calibrated_compare(a[comp], b[comp], v[comp], atol=COMPLEMENT_ULPS)
+            assert ok, (name, comp, rec["by_decade_below_peak"])
+    e_cpu = relerr(T_v, T_o)
+    assert relerr(T, T_o) < (1.3e-7 if e_cpu <= 1.3e-7 else 10.0 * e_cpu)
+    for a, b, v in zip(c.get_rates(), g.get_rates(), gv.get_rates()):
+        comps = range(a.shape[0]) if a.ndim == 4 else [None]
+        for comp in comps:
+            rec, ok = calibrated_compare(a if comp is None else a[comp], b if comp is None else b[comp], v if comp is None else v[comp])
+            assert ok, rec["by_decade_below_peak"]
     # device rad_ini with all three SEDs against the oracle's tables
     c2 = c2ray_b200.from_problem(p)
     for sed in range(3):
