@@ -58,7 +58,7 @@ def test_golden_evolve3d():
     assert relerr(T, G["T_cfg3"]) < 1.3e-7
     for a, key in zip(c.get_rates(), ("rates_phih_cfg3", "rates_phihe_cfg3", "rates_phiheat_cfg3")):
         b = G[key]
-        assert relerr(a, b, 1e-6 * np.abs(b).max()) < 1e-8, key
+        assert relerr(a, b, 1e-300) < 1e-8, key   # pure relative
     c.close()
 
 

@@ -215,7 +215,7 @@ def test_pass_all_sources(cfg, n, nsrc, iso, sub):
         for a, b, name in zip(rg, ro, ("phih", "phihe", "phiheat")):
             if iso and name == "phiheat":
                 continue
-            assert relerr(a, b, 1e-6 * np.abs(b).max() + 1e-300) < TOL, name
+            assert relerr(a, b, 1e-300) < TOL, name  # pure relative wherever the oracle's value is non-zero
             nz = b != 0
             assert np.array_equal(a != 0, nz), name
         nb = [c.do_source(p["dt"], ns, 1) for ns in range(1, len(p["NormFlux"]) + 1)]
