@@ -250,6 +250,23 @@ int upload_band_const(c2ray_ctx* c) {
   }
   for (int q = 0; q < NumFreqBnd; q++) bc[q].dead_bb = INFINITY;  // until tables are packed (pack_tables)
   CK(cudaMemcpyToSymbol(d_band, bc, sizeof(c->h_band)));
+#if C2RAY_TABLOG
+  {
+    // tau_table_position's mantissa table and series coefficients (c2ray_photo.cuh), formed in long double
+    const long double K = 1.0L / (long double)dlogtau, l10e = 1.0L / logl(10.0L);
+    static double2 tab[256];
+    for (int i = 0; i < 256; i++) {
+      const double ci = 1.0 + (i + 0.5) / 256.0;
+      const double ri = (double)(1.0L / (long double)ci);
+      tab[i].x = ri;
+      tab[i].y = (double)(1.0L + (log10l(1.0L / (long double)ri) - (long double)minlogtau) * K);
+    }
+    const double pc[7] = {(double)(log10l(2.0L) * K), (double)(l10e * K), (double)(-l10e * K / 2.0L), (double)(l10e * K / 3.0L),
+                          (double)(-l10e * K / 4.0L), (double)(l10e * K / 5.0L), (double)(-l10e * K / 6.0L)};
+    CK(cudaMemcpyToSymbol(g_postab, tab, sizeof(tab)));
+    CK(cudaMemcpyToSymbol(d_posc, pc, sizeof(pc)));
+  }
+#endif
   return 0;
 }
 
@@ -552,7 +569,7 @@ int sweep_all(c2ray_ctx* c) {
             // Fewer cells than resident threads: the launch is bound by the latency of one update's dependency chain,
             // not by throughput, so 2..16 lanes share a cell (see k_sweep_shell) -- as many as still fit the resident
             // threads (x sweep_lanes_fill).  sweep_lanes_mode 0: the round-1 rule (8 lanes below a quarter wave).
-            const long long resident = 148LL * 128 * (multi_sed ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS);
+            const long long resident = 148LL * 128 * C2RAY_SWEEP_MINBLOCKS_SPLIT;  // of the LANES > 1 instances
             int lanes = 1;
             if (c->sweep_split) {
               if (c->sweep_lanes_mode == 0) {

@@ -218,13 +218,21 @@ __global__ void k_cell_records_level(const Slot* __restrict__ slots, const int* 
 #ifndef C2RAY_SWEEP_MINBLOCKS_MULTI
 #define C2RAY_SWEEP_MINBLOCKS_MULTI 5
 #endif
+// The LANES > 1 instances only ever run in launches below one resident wave, where occupancy buys nothing and the
+// latency of the one chain is everything: they get 128 registers (4 CTAs/SM, no spills).  One source at 128^3:
+// 51.2 -> 45.2 ms of sweeps per time step with every instance at 4 CTAs/SM, while the full-wave launches of configs[1]
+// and [2] lose 6 % there (profiles/r2_ab10_unroll.log) -- hence per instance.
+#ifndef C2RAY_SWEEP_MINBLOCKS_SPLIT
+#define C2RAY_SWEEP_MINBLOCKS_SPLIT 4
+#endif
 // LANES (1 or a power of two <= 32): lanes of a warp that share one cell, each taking every LANES-th frequency band.
 // One update is a dependent chain of ~9 k instructions, ~25 us for a warp on its own; a launch that cannot fill the
 // machine (the inner shells, few sources) is bound by that latency, not by throughput, and finishes LANES times sooner
 // when the chain is cut into LANES pieces.  The geometry part is computed redundantly by the sharing lanes; lane 0 of a
 // cell writes.  Launches with more cells than resident threads use LANES = 1.
 template <bool ISO, bool MULTI, int LANES>
-__global__ void __launch_bounds__(128, MULTI ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS)
+__global__ void __launch_bounds__(128, LANES > 1 ? C2RAY_SWEEP_MINBLOCKS_SPLIT
+                                                : (MULTI ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS))
 k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot, SweepGeom g,
               GridPtrs G, double* __restrict__ scratch, int r, double* __restrict__ lossbuf) {
   // lossbuf != nullptr (deterministic mode, one source at a time): every cell of the shell writes its photon-loss
@@ -234,6 +242,9 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
   // while this one drains (its threads decode their cell, test the box and fetch the cell record, then wait below
   // before they touch the shell scratch).  Without the launch attribute both instructions are no-ops.
   asm volatile("griddepcontrol.launch_dependents;");
+#if C2RAY_TABLOG
+  postab_stage();  // 4 KB, L2-resident; before griddepcontrol.wait, so it overlaps the previous shell's tail
+#endif
   const int nact = tot->nactive;
   const int ncell = shell_cells(r);
   const long long total = (long long)nact * ncell * LANES;
@@ -756,6 +767,9 @@ __global__ void k_total_rates(const double* __restrict__ ndens, const double* __
 // ------------------------------------------------------------------------------------------------
 __global__ void k_photoion_batch(int n, const double* __restrict__ col6, const double* __restrict__ vol, double nf0,
                                  double nf1, double nf2, const double* __restrict__ i_state, double* __restrict__ out6) {
+#if C2RAY_TABLOG
+  postab_stage();
+#endif
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const double* q = col6 + 6 * (size_t)t;

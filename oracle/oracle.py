@@ -21,7 +21,8 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 def build(force=False):
     src = os.path.join(HERE, "c2ray_oracle.cpp")
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src) or \
-            not os.path.exists(os.path.join(HERE, "libc2ray_oracle_fma.so")):
+            not os.path.exists(os.path.join(HERE, "libc2ray_oracle_fma.so")) or \
+            not os.path.exists(os.path.join(HERE, "libc2ray_oracle_assoc.so")):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return LIB
 

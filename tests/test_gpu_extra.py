@@ -8,7 +8,7 @@ import pytest
 import c2ray_b200
 from c2ray_b200 import capi
 from oracle import oracle as O
-from common import (oracle_setup, oracle_grid, relerr, frac_err, partially_ionized_state, load_oracle_variant, setup_variant,
+from common import (oracle_setup, oracle_grid, relerr, frac_err, partially_ionized_state, load_oracle_variant, load_oracle_variants, setup_variant, temperature_bound,
                     calibrated_compare, COMPLEMENT_ULPS)
 
 pytestmark = pytest.mark.gpu
@@ -209,21 +209,24 @@ def test_all_three_seds():
     # oracle too: tools/diag_evolve.py), i.e. they sit on a limit cycle that amplifies last-digit differences during the
     # intermediate global iterations.  How far is measured on the reference's own two CPU builds and allowed for, decade by
     # decade of the value (tests/common.py calibrated_compare; pure relative 1e-8 where the two CPU builds agree).
-    gv = setup_variant(load_oracle_variant(), p)
-    sv = gv.evolve3d(p["dt"])
-    assert sv["niter"] == so["niter"]
-    xh_v, xhe_v, T_v = gv.get_state()
-    for name, a, b, v in (("xh", xh, xh_o, xh_v), ("xhe", xhe, xhe_o, xhe_v)):
+    states_v, rates_v = [], []
+    for V in load_oracle_variants():   # FMA-contracted and reassociating builds of the oracle source
+        gv = setup_variant(V, p)
+        sv = gv.evolve3d(p["dt"])
+        assert sv["niter"] == so["niter"]
+        states_v.append(gv.get_state()); rates_v.append(gv.get_rates())
+    for k, (name, a, b) in enumerate((("xh", xh, xh_o), ("xhe", xhe, xhe_o))):
         for comp in range(a.shape[0]):
-            rec, ok = calibrated_compare(a[comp], b[comp], v[comp], atol=COMPLEMENT_ULPS)
-            assert ok, (name, comp, rec["by_decade_below_peak"])
-    e_cpu = relerr(T_v, T_o)
-    assert relerr(T, T_o) < (1.3e-7 if e_cpu <= 1.3e-7 else 10.0 * e_cpu)
-    for a, b, v in zip(c.get_rates(), g.get_rates(), gv.get_rates()):
+            rec, ok = calibrated_compare(a[comp], b[comp], [s[k][comp] for s in states_v], atol=COMPLEMENT_ULPS)
+            assert ok, (name, comp, rec["violations"], rec["failed_decades"])
+    e_cpu = max(relerr(s[2], T_o) for s in states_v)
+    assert relerr(T, T_o) < temperature_bound(e_cpu)
+    for k, (a, b) in enumerate(zip(c.get_rates(), g.get_rates())):
         comps = range(a.shape[0]) if a.ndim == 4 else [None]
         for comp in comps:
-            rec, ok = calibrated_compare(a if comp is None else a[comp], b if comp is None else b[comp], v if comp is None else v[comp])
-            assert ok, rec["by_decade_below_peak"]
+            v = [r[k] for r in rates_v]
+            rec, ok = calibrated_compare(a if comp is None else a[comp], b if comp is None else b[comp], v if comp is None else [x[comp] for x in v])
+            assert ok, (k, comp, rec["violations"], rec["failed_decades"], rec["zero_pattern_mismatch"])
     # device rad_ini with all three SEDs against the oracle's tables
     c2 = c2ray_b200.from_problem(p)
     for sed in range(3):
