@@ -414,7 +414,7 @@ __global__ void k_pack_tail(const SweepTotals* gtot, int ngroups, SweepTotals* t
   const int t = threadIdx.x;
   if (t == 0) {
     SweepTotals a;
-    a.photon_loss = 0.0; a.sum_nbox = 0; a.updates = 0; a.nactive = 0; a.pad = 0;
+    a.photon_loss = 0.0; a.sum_nbox = 0; a.updates = 0; a.nactive = 0;
     for (int g = 0; g < ngroups; g++) { a.photon_loss += gtot[g].photon_loss; a.sum_nbox += gtot[g].sum_nbox; a.updates += gtot[g].updates; }
     *tot = a;
     tail[0] = a.photon_loss;
@@ -581,8 +581,10 @@ int sweep_all(c2ray_ctx* c) {
             }
             const long long items = cells * lanes;
 #if C2RAY_NOSTRIDE
-            const int blocks = (int)((items + 127) / 128);   // one work item per thread
+            const unsigned cta = lanes > 1 ? 128u : (unsigned)C2RAY_SWEEP_THREADS;
+            const int blocks = (int)((items + cta - 1) / cta);   // one work item per thread
 #else
+            const unsigned cta = 128u;
             const int blocks = (int)std::min<long long>((items + 127) / 128, max_blocks);
 #endif
             // the predecessor in this group's stream is the previous shell of the same level (not k_decide): overlap
@@ -591,7 +593,7 @@ int sweep_all(c2ray_ctx* c) {
             const bool pdl = c->sweep_pdl && ngroups == 1 && r > r_lo;
 #define SWEEP(ISO, MULTI, LANES)                                                                                              \
   do {                                                                                                                        \
-    CK(launch_overlapped(k_sweep_shell<ISO, MULTI, LANES>, (unsigned)blocks, 128u, c->gstream[q], pdl, c->d_slots + goff[q],  \
+    CK(launch_overlapped(k_sweep_shell<ISO, MULTI, LANES>, (unsigned)blocks, cta, c->gstream[q], pdl, c->d_slots + goff[q],  \
                          (const int*)(c->d_active + goff[q]), c->d_gtot + q, g, G,                                            \
                          c->d_scratch + (size_t)goff[q] * slot_stride, r, lossbuf));                                          \
     c->launches++; c->sweep_launches++;                                                                                        \

@@ -15,24 +15,30 @@ namespace c2 {
 // ------------------------------------------------------------------------------------------------
 // Sweep bookkeeping
 // ------------------------------------------------------------------------------------------------
-struct Slot {          // one source being traced (evolve_source.F90:66-238 local state)
+// Two 128-byte lines per slot.  Every thread of a shell launch reads the first (and again after its band loop); the
+// second takes the photon-loss atomics of the boundary cells.  In one line, each atomic threw the line out of the issuing
+// SM's L1 and the next reader queued behind the atomics at the L2 -- the same for SweepTotals::nactive next to the update
+// counter, where the first instruction after the load held 7.6 % of the kernel's warp time
+// (profiles/r2c_ncu_sweep_cfg1_stalls.txt).
+struct alignas(128) Slot {  // one source being traced (evolve_source.F90:66-238 local state)
   double nflux[3];     // NormFlux, NormFluxPL, NormFluxQPL of the source
   double total_flux;   // :122-128
-  double loss;         // photon_loss_src
   int src;             // 0-based source number
   int s[3];            // srcpos (1-based mesh position)
   int lo[3], hi[3];    // current sub-box reach: last_l = srcpos - lo, last_r = srcpos + hi (:143-144)
   int nbox;
   int active;
+  alignas(128) double loss;  // photon_loss_src
 };
+static_assert(sizeof(Slot) == 256, "Slot: one read-mostly line, one line for the atomics");
 
 struct SweepTotals {
   double photon_loss;               // photon_loss(1), evolve_source.F90:233
   unsigned long long sum_nbox;      // :236
   unsigned long long updates;       // evolve0D calls that did work
-  int nactive;
-  int pad;
+  alignas(128) int nactive;         // written by k_slots_init / k_decide only
 };
+static_assert(sizeof(SweepTotals) == 256, "SweepTotals: counters and nactive in separate lines");
 
 struct SweepGeom {
   int L[3], R[3];   // lastpos_l / lastpos_r reach (:103-105)
@@ -225,14 +231,18 @@ __global__ void k_cell_records_level(const Slot* __restrict__ slots, const int* 
 #ifndef C2RAY_SWEEP_MINBLOCKS_SPLIT
 #define C2RAY_SWEEP_MINBLOCKS_SPLIT 4
 #endif
+// threads per CTA of the LANES == 1 instances (the LANES > 1 instances keep 128)
+#ifndef C2RAY_SWEEP_THREADS
+#define C2RAY_SWEEP_THREADS 128
+#endif
 // LANES (1 or a power of two <= 32): lanes of a warp that share one cell, each taking every LANES-th frequency band.
 // One update is a dependent chain of ~9 k instructions, ~25 us for a warp on its own; a launch that cannot fill the
 // machine (the inner shells, few sources) is bound by that latency, not by throughput, and finishes LANES times sooner
 // when the chain is cut into LANES pieces.  The geometry part is computed redundantly by the sharing lanes; lane 0 of a
 // cell writes.  Launches with more cells than resident threads use LANES = 1.
 template <bool ISO, bool MULTI, int LANES>
-__global__ void __launch_bounds__(128, LANES > 1 ? C2RAY_SWEEP_MINBLOCKS_SPLIT
-                                                : (MULTI ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS))
+__global__ void __launch_bounds__(LANES > 1 ? 128 : C2RAY_SWEEP_THREADS,
+                                  LANES > 1 ? C2RAY_SWEEP_MINBLOCKS_SPLIT : (MULTI ? C2RAY_SWEEP_MINBLOCKS_MULTI : C2RAY_SWEEP_MINBLOCKS))
 k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot, SweepGeom g,
               GridPtrs G, double* __restrict__ scratch, int r, double* __restrict__ lossbuf) {
   // lossbuf != nullptr (deterministic mode, one source at a time): every cell of the shell writes its photon-loss
@@ -242,10 +252,10 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
   // while this one drains (its threads decode their cell, test the box and fetch the cell record, then wait below
   // before they touch the shell scratch).  Without the launch attribute both instructions are no-ops.
   asm volatile("griddepcontrol.launch_dependents;");
+  const int nact = tot->nactive;  // (requested before the barrier below: its latency passes under the staging)
 #if C2RAY_TABLOG
   postab_stage();  // 4 KB, L2-resident; before griddepcontrol.wait, so it overlaps the previous shell's tail
 #endif
-  const int nact = tot->nactive;
   const int ncell = shell_cells(r);
   const long long total = (long long)nact * ncell * LANES;
   const int lane_j = LANES > 1 ? (int)(threadIdx.x & (LANES - 1)) : 0;
