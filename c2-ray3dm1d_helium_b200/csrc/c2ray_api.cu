@@ -944,6 +944,21 @@ static int init_device_state(c2ray_ctx* c) {
   if (const char* e = getenv("C2RAY_SWEEP_SPLIT")) c->sweep_split = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_PDL")) c->sweep_pdl = atoi(e);
   if (const char* e = getenv("C2RAY_DEAD_BANDS")) c->dead_bands = atoi(e);
+  {
+    // Shared-memory carve-out of the sweep instances, percent of the SM's 228 KB; what is left is their L1.  They need
+    // 5 x (4 KB + 1 KB reserved); the driver's default leaves more to shared memory than that.  Measured
+    // (profiles/r2_ab17_carveout.log): 10 % 12.69 ms per configs[1] pass / 249.2 ms per configs[2] pass, default 12.85 / 253.6,
+    // 50 % 13.05 / 264.8, 100 % 13.73 / 281.3.
+    int pct = 10;
+    if (const char* e = getenv("C2RAY_SWEEP_CARVEOUT")) pct = atoi(e);
+    if (pct >= 0) {
+#define CARVE(ISO, MULTI, LANES) CK(cudaFuncSetAttribute(k_sweep_shell<ISO, MULTI, LANES>, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
+#define CARVE5(ISO, MULTI) CARVE(ISO, MULTI, 1); CARVE(ISO, MULTI, 2); CARVE(ISO, MULTI, 4); CARVE(ISO, MULTI, 8); CARVE(ISO, MULTI, 16)
+      CARVE5(false, false); CARVE5(false, true); CARVE5(true, false); CARVE5(true, true);
+#undef CARVE5
+#undef CARVE
+    }
+  }
   if (const char* e = getenv("C2RAY_SWEEP_LANES_MODE")) c->sweep_lanes_mode = atoi(e);
   if (const char* e = getenv("C2RAY_SWEEP_LANES_FILL")) c->sweep_lanes_fill = std::max(0.1, atof(e));
   if (const char* e = getenv("C2RAY_SPARSE_RECORDS")) c->sparse_records = atoi(e);
