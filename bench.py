@@ -322,6 +322,8 @@ def run_b200(args):
                     "fp64_achieved_tflops": fp64_tflops, "fp64_peak_tflops_measured": fp64_peak,
                     "fp64_frac": (fp64_tflops / fp64_peak) if fp64_tflops else None,
                     "fp64_flops_per_update": flops_per_update, "figures_source": fig.get("source"),
+                    # the unit nearest its own peak in the committed capture (not a throughput roofline: DESIGN section 3)
+                    "busiest_unit_in_capture": fig.get("busiest_unit"),
                     "hbm_achieved_gbs": sweep_gbs, "hbm_peak_gbs": peak, "hbm_frac": sweep_gbs / peak, "hbm_peak_source": peak_src,
                     "hbm_algorithmic_bytes_per_update": BYTES_PER_UPDATE,
                     "traffic": (traffic_per_update * launch_updates) if traffic_per_update else None,

@@ -98,7 +98,17 @@ __device__ __forceinline__ void postab_stage() {
 __device__ __forceinline__ TauPos tau_table_position(double tau) {
   static_assert(minlogtau == -20.0 && dlogtau == 24.0 / 2000.0, "d_lit[6] holds 1/dlogtau");
 #if C2RAY_TABLOG
+#ifndef C2RAY_POS_INTCLAMP
+#define C2RAY_POS_INTCLAMP 1
+#endif
+#if C2RAY_POS_INTCLAMP
+  // The clamp max(1e-20, tau) of :288 is applied to the result instead (an fmax on doubles sits 26 cycles in front of
+  // everything else, tools/latency_probe.cu): tau <= 1e-20 (tau = 0 in the source cell) gives odpos < 1 -- hugely
+  // negative but finite for 0 and denormals, whose exponent field reads as 2^-1023 -- and is put on row 1, residual 0.
+  const double x = tau;
+#else
   const double x = fmax(d_lit[3], tau);
+#endif
   const int hi = __double2hiint(x);
   const double2 ent = postab_smem()[(hi >> 12) & 0xff];
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
@@ -115,8 +125,14 @@ __device__ __forceinline__ TauPos tau_table_position(double tau) {
   const double odpos = fma(lt - minlogtau, d_lit[6], 1.0);
 #endif
   TauPos p;
+#if C2RAY_TABLOG && C2RAY_POS_INTCLAMP
+  const int raw = (int)odpos;
+  p.ipos = min(max(raw, 1), NumTau);
+  p.residual = raw < 1 ? 0.0 : odpos - (double)p.ipos;
+#else
   p.ipos = min((int)odpos, NumTau);
   p.residual = odpos - (double)p.ipos;
+#endif
   return p;
 }
 
