@@ -205,7 +205,7 @@ def run_reference(args):
             "config": config_dict(args.workload, p, n_gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": "per step: " + cs.describe()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -352,13 +352,30 @@ def run_b200(args):
             upd, dt, t_rt = cs.run()
             line["cpu_baseline"] = {"value": upd / dt, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": cs.describe(),
                                     "rt_updates_per_s": upd / t_rt, "chem_cells_per_s": N3 / cs.t_chem}
-        print(json.dumps(line))
+        emit(line)
     c.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else that lands on fd 1 meanwhile (NCCL prints its
+    version banner there from C) has been sent to stderr, so that the driver reads exactly one line."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
