@@ -55,6 +55,46 @@ def test_photoion_rates_batch(iso, with_qpl):
     c.close()
 
 
+def test_photoion_rates_table_position_edges():
+    """The table position of radiation_photoionrates.f90:282-306 at its edges: optical depth 0 (source cell), below and at
+    the 1e-20 clamp, denormal incoming columns, exact table rows (tau = 10^(-20 + k*0.012)), just either side of a row, beyond the
+    last row (tau > 1e4: both interpolation rows are row NumTau), optically thin and thick cells at each of them."""
+    p = synth.make_problem(1, n=8, num_src=1)
+    c = c2ray_b200.from_problem(p, tables=oracle_setup(p))
+    sig = 6.30e-18   # hydrogen cross section at its edge, order of magnitude: puts tau_in of band 1 on the values below
+    taus = [0.0, 5e-324 * sig, 1e-310 * sig, 1e-30, 0.999999e-20, 1e-20, 1.000001e-20, 3e-20, 1e-12, 1e-7, 0.9999e-4, 1.0001e-4,
+            0.5, 1.0, 2.0 - 1e-12, 2.0, 40.0, 699.0, 701.0, 9999.0, 1e4, 1.0001e4, 1e5, 1e8]
+    rows = [10.0 ** (-20.0 + k * 0.012) for k in (1, 2, 500, 1000, 1500, 1665, 1666, 1667, 1999, 2000)]
+    rows = [t * f for t in rows for f in (1.0 - 3e-16, 1.0, 1.0 + 3e-16)]
+    lin, dcol = [], []
+    for t in taus + rows:
+        for d in (1e-12, 1e-9, 3e-8, 1e-5, 0.3, 5.0, 200.0):   # the cell's own optical depth, thin to thick (an exact zero
+            # is 0/0 in the species shares of :787-825 -- NaN in the reference too -- and cannot occur: ndens, path > 0)
+            lin.append(t / sig); dcol.append(d / sig)
+    lin = np.array(lin); dcol = np.array(dcol)
+    keep = np.ones(lin.size, dtype=bool)
+    for f in (1.0, 0.08, 0.003):   # a cell column that the incoming one absorbs in rounding is the same 0/0
+        keep &= (lin * f + dcol * f) != lin * f
+    lin, dcol = lin[keep], dcol[keep]
+    n = lin.size
+    assert n > 350
+    col6 = np.empty((n, 6))
+    for k, f in enumerate((1.0, 0.08, 0.003)):   # H, He0, He1 columns in fixed proportions
+        col6[:, 2 * k] = lin * f
+        col6[:, 2 * k + 1] = lin * f + dcol * f
+    vol = np.full(n, 1e63); i_state = np.full(n, 1e-3)
+    nflux = [1.0e5, 0.0, 0.0]
+    got = c.photoion_rates(col6, vol, nflux, i_state)
+    ref = O.photoion_rates_batch(col6, vol, nflux, i_state)
+    assert np.isfinite(got).all()
+    scale = np.abs(ref).max(axis=0)
+    for k in range(6):
+        err = np.abs(got[:, k] - ref[:, k]) / np.maximum(np.abs(ref[:, k]), 1e-6 * scale[k] + 1e-300)
+        assert err.max() < TOL, (k, err.max(), int(np.argmax(err)), lin[np.argmax(err)] * sig, dcol[np.argmax(err)] * sig)
+    assert ((got == 0.0) == (ref == 0.0)).all()   # exact zeros (dead rows beyond tau = 700) in the same places
+    c.close()
+
+
 def _random_states(n, seed):
     rng = np.random.default_rng(seed)
     x1 = 10.0 ** rng.uniform(-8, -0.001, n); a = 10.0 ** rng.uniform(-8, -0.31, n); b = a * 10.0 ** rng.uniform(-6, -0.1, n)
