@@ -214,7 +214,8 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
   const double dtau = NSP == 3 ? (tcHI + tcHeI + tcHeII) : (NSP == 2 ? tcHI + tcHeI : tcHI);
 #if !defined(C2RAY_MULTI_SED_INNER) && C2RAY_DEAD_BANDS
   // (the single-SED kernels read the black body's threshold from the band record they have in cache anyway)
-  if (tau_in >= (pk_single ? d_dead[sed_single][q] : BANDREC(q).dead_bb)) return;  // every row this band would read is exactly zero
+  // (the black body's threshold rides in the band record, the constant-cache line this step reads anyway)
+  if (tau_in >= ((pk_single && sed_single != 0) ? d_dead[sed_single][q] : BANDREC(q).dead_bb)) return;  // every row this band would read is exactly zero
 #endif
   const double tau_out = tau_in + dtau;
 #else
