@@ -197,9 +197,10 @@ struct CellCols {
 
 // One frequency band (1-based b, NSP species absorb in it) for every active SED.
 // MULTI = false: only the black-body SED exists in this run; NFlux is then factored out of the band loop.
-template <bool ISO, int NSP, bool MULTI, bool NEED_IN = true>
+template <bool ISO, int NSP, bool MULTI, bool NEED_IN = true, bool SCALED = false>
 __device__ __forceinline__ void band_step(int b, const CellCols& c, const double nflux[3], unsigned actmask,
-                                          PhotAcc& A, const double* __restrict__ pk_single = nullptr, int sed_single = 0) {
+                                          PhotAcc& A, const double* __restrict__ pk_single = nullptr, int sed_single = 0,
+                                          double nf_single = 1.0) {
   const int q = b - 1;
   const double sHI = BANDREC(q).sigma_HI;
   const double sHeI = NSP >= 2 ? BANDREC(q).sigma_HeI : 0.0;
@@ -256,7 +257,7 @@ __device__ __forceinline__ void band_step(int b, const CellCols& c, const double
       if (!((actmask >> s) & 1u) || b < d_run.sed[s].lo || b > d_run.sed[s].hi) continue;
     }
     const double* __restrict__ pk = MULTI ? d_run.sed[s].packed : (pk_single ? pk_single : d_run.sed[0].packed);
-    const double NFlux = MULTI ? nflux[s] : 1.0;
+    const double NFlux = MULTI ? nflux[s] : (SCALED ? nf_single : 1.0);  // SCALED: one SED of a multi-SED source, its flux applied per band
     if (ISO) {  // photo_lookuptable :390-425 on the photo-only copy of the tables
       const double* pi = pk + PK_ISO_OFF + (size_t)q * PK_ROWS + pin.ipos;
       const double phi_in = NFlux * lerp(__ldg(pi), __ldg(pi + 1), pin.residual);
@@ -394,12 +395,24 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
     // copies of the table look-ups in every band for a sum that usually has one term (the black body ends at band
     // 33-36, PL / QPL start at 38).
     PhotAcc T = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#ifndef C2RAY_MULTI_SCALED
+#define C2RAY_MULTI_SCALED 1
+#endif
 #pragma unroll 1
     for (int s = 0; s < 3; s++) {
       const int lo = d_run.sed[s].lo, hi = d_run.sed[s].hi;
       const double nf = nflux[s];
       if (hi < lo || !(nf > 0.0)) continue;
       const double* __restrict__ pk = d_run.sed[s].packed;
+#if C2RAY_MULTI_SCALED
+      // the SED's flux is applied inside the band step (five multiplications per band) instead of to a second set of ten
+      // accumulators afterwards: 20 registers less in a kernel that spills
+      if (lo <= NumBndin1 && lane_j == 0) band_step<ISO, 1, false, NEED_IN, true>(1, c, nflux, 1u, T, pk, s, nf);
+      for (int b = max(lo, NumBndin1 + 1) + lane_j; b <= min(hi, NumBndin1 + NumBndin2); b += LANES)
+        band_step<ISO, 2, false, NEED_IN, true>(b, c, nflux, 1u, T, pk, s, nf);
+      for (int b = max(lo, NumBndin1 + NumBndin2 + 1) + lane_j; b <= hi; b += LANES)
+        band_step<ISO, 3, false, NEED_IN, true>(b, c, nflux, 1u, T, pk, s, nf);
+#else
       PhotAcc B = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       if (lo <= NumBndin1 && lane_j == 0) band_step<ISO, 1, false, NEED_IN>(1, c, nflux, 1u, B, pk, s);
       for (int b = max(lo, NumBndin1 + 1) + lane_j; b <= min(hi, NumBndin1 + NumBndin2); b += LANES)
@@ -412,6 +425,7 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
         T.f_heat = fma(nf, B.f_heat, T.f_heat);
         T.s1 = fma(nf, B.s1, T.s1); T.s2 = fma(nf, B.s2, T.s2); T.s3 = fma(nf, B.s3, T.s3); T.s4 = fma(nf, B.s4, T.s4);
       }
+#endif
     }
     scale_out = 1.0;
     return T;
