@@ -484,7 +484,6 @@ int sweep_all(c2ray_ctx* c) {
     ngroups = c->par.deterministic ? 1 : std::max(1, std::min(c->sweep_groups, std::min(c->slots_cap, c->n_mine)));
     const int region = c->par.deterministic ? 1 : c->slots_cap / ngroups;  // slots per stream group
     const int batch = region * ngroups;                                     // sources in flight at a time
-    static const int max_blocks = [] { const char* e = getenv("C2RAY_SWEEP_MAXBLOCKS"); return e ? std::max(1, atoi(e)) : 148 * 16; }();
     // A source whose PL and QPL fluxes are zero (or whose tables are absent) contributes through the black-body
     // tables only and takes the single-SED kernel, whatever other sources need: in a -DQUASARS run with QPL flux
     // on a few bright sources the rest do not pay for the three-SED loop.  The list is ordered single-SED sources
@@ -580,13 +579,8 @@ int sweep_all(c2ray_ctx* c) {
               }
             }
             const long long items = cells * lanes;
-#if C2RAY_NOSTRIDE
             const unsigned cta = lanes > 1 ? 128u : (unsigned)C2RAY_SWEEP_THREADS;
             const int blocks = (int)((items + cta - 1) / cta);   // one work item per thread
-#else
-            const unsigned cta = 128u;
-            const int blocks = (int)std::min<long long>((items + 127) / 128, max_blocks);
-#endif
             // the predecessor in this group's stream is the previous shell of the same level (not k_decide): overlap
             // Measured: +6 % on a single source (one group: nothing else fills the draining tail), -0.7 % with two
             // groups on two streams (they already overlap each other's tails) -> only used with a single group.

@@ -218,9 +218,6 @@ __global__ void k_cell_records_level(const Slot* __restrict__ slots, const int* 
 #ifndef C2RAY_SWEEP_MINBLOCKS
 #define C2RAY_SWEEP_MINBLOCKS 5
 #endif
-#ifndef C2RAY_NOSTRIDE
-#define C2RAY_NOSTRIDE 1   // one work item per thread (0: grid-stride loop over a capped grid)
-#endif
 #ifndef C2RAY_SWEEP_MINBLOCKS_MULTI
 #define C2RAY_SWEEP_MINBLOCKS_MULTI 5
 #endif
@@ -265,12 +262,13 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
   constexpr bool iso = ISO;
   const int m0 = d_run.mesh[0], m1 = d_run.mesh[1], m2 = d_run.mesh[2];
   unsigned int done = 0;
-#if C2RAY_NOSTRIDE
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, once = 1; once && t < total; once = 0) {
-#else
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-#endif
+  {
+    // One work item per thread.  No thread leaves early: threads beyond the work, and threads whose cell lies outside
+    // its source's sub-box, run along on harmless values (item 0 / unit columns) with `inbox` false, so that the band
+    // loop below sits in convergent code.
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = t0 < total;
+    const long long t = in_range ? t0 : 0;
     const long long item = LANES > 1 ? t / LANES : t;   // the LANES lanes of an aligned group share the item
     const int a = (int)(item / ncell);
     const int c = (int)(item - (long long)a * ncell);
@@ -278,23 +276,24 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     Slot& S = slots[sid];
     int di, dj, dk;
     shell_decode(c, r, di, dj, dk);
-    if (di < -S.lo[0] || di > S.hi[0] || dj < -S.lo[1] || dj > S.hi[1] || dk < -S.lo[2] || dk > S.hi[2]) {
-      if (lossbuf && lane_j == 0) lossbuf[c] = 0.0;
-      continue;
-    }
+    const bool inbox = in_range && !(di < -S.lo[0] || di > S.hi[0] || dj < -S.lo[1] || dj > S.hi[1] || dk < -S.lo[2] || dk > S.hi[2]);
+    if (in_range && !inbox && lossbuf && lane_j == 0) lossbuf[c] = 0.0;
     double* cur = scratch + sid * slot_stride + (size_t)par * 3 * g.cap;
     const double* prev = scratch + sid * slot_stride + (size_t)(par ^ 1) * 3 * g.cap;
-
     const int i0 = S.s[0], j0 = S.s[1], k0 = S.s[2];
     const size_t p = (size_t)wrap0(i0 + di, m0) + (size_t)m0 * ((size_t)wrap0(j0 + dj, m1) + (size_t)m1 * wrap0(k0 + dk, m2));
-    const double2 rec0 = ld2(G.cellrec + p * (ISO ? CELLREC_ISO : CELLREC));      // xh_av(0) n, xhe_av(0) n
-    const double2 rec1 = ld2(G.cellrec + p * (ISO ? CELLREC_ISO : CELLREC) + 2);  // xhe_av(1) n, -
-
+    double2 rec0 = make_double2(1.0, 1.0), rec1 = make_double2(1.0, 0.0);
+    if (inbox) {
+      rec0 = ld2(G.cellrec + p * (ISO ? CELLREC_ISO : CELLREC));      // xh_av(0) n, xhe_av(0) n
+      rec1 = ld2(G.cellrec + p * (ISO ? CELLREC_ISO : CELLREC) + 2);  // xhe_av(1) n, -
+    }
     // Everything above reads only what is constant within a sub-box level (slots, active list, cell records).  From
     // here on the previous shell's column densities are read and the buffer it is still reading is overwritten.
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    double cin_H, cin_He0, cin_He1, path, vol_ph;
-    if (r == 0) {  // evolve_point.F90:140-150
+    double cin_H = 1.0, cin_He0 = 1.0, cin_He1 = 1.0, path = 1.0, vol_ph = 1.0;
+    if (!inbox) {
+      // (nothing to interpolate)
+    } else if (r == 0) {  // evolve_point.F90:140-150
       cin_H = 0.0; cin_He0 = 0.0; cin_He1 = 0.0;
       path = FL(0.5f) * d_run.dr[0];
       vol_ph = d_run.dr[0] * d_run.dr[1] * d_run.dr[2];
@@ -388,60 +387,65 @@ k_sweep_shell(Slot* slots, const int* __restrict__ active_list, SweepTotals* tot
     const double cout_H = cin_H + rec0.x * path * (1.0 - abu_he);
     const double cout_He0 = cin_He0 + rec0.y * path * abu_he;
     const double cout_He1 = cin_He1 + rec1.x * path * abu_he;
-    if (lane_j == 0) { cur[c] = cout_H; cur[g.cap + c] = cout_He0; cur[2 * g.cap + c] = cout_He1; }
+    if (inbox && lane_j == 0) { cur[c] = cout_H; cur[g.cap + c] = cout_He0; cur[2 * g.cap + c] = cout_He1; }
 
     PhotOut phi = {0, 0, 0, 0, 0, 0};
-    if (cin_H < max_coldensh) {  // :250-270
+    const bool do_bands = inbox && cin_H < max_coldensh;  // :250-270
+    // The band loop runs in convergent code -- every lane of the warp enters it when any lane has a cell to do, lanes
+    // without one on harmless columns -- so that the compiler may keep the band index, and with it the band constants,
+    // in the uniform datapath.
+    if (__any_sync(0xffffffffu, do_bands)) {
       double scale;
       PhotAcc A = photoion_bands<ISO, MULTI, LANES, false>(cin_H, cout_H, cin_He0, cout_He0, cin_He1, cout_He1, S.nflux, scale, lane_j);
-      if (LANES > 1) reduce_bands<ISO, LANES>(A, lane_mask);  // the branch above is uniform over the lanes of a cell
-      // the cell's secondary-ionisation factors are only needed now: loading them after the band loop keeps twelve
-      // registers free while it runs
-      // (the record's address is formed again from the cell index behind an optimisation barrier, so that only the
-      // index stays live across the loop)
-      size_t p2 = p;
-      asm volatile("" : "+l"(p2));
-      const double* rec = G.cellrec + p2 * (ISO ? CELLREC_ISO : CELLREC);
-      SecIon yR = {0, 0, 0, 0, 0, 0};
-      if (!iso) {
-        const double2 y0 = ld2(rec + 4), y1 = ld2(rec + 6), y2 = ld2(rec + 8);
-        yR.y1R0 = y0.x; yR.y1R1 = y0.y; yR.y1R2 = y1.x; yR.y2R0 = y1.y; yR.y2R1 = y2.x; yR.y2R2 = y2.y;
+      if (LANES > 1) reduce_bands<ISO, LANES>(A, lane_mask);  // (do_bands is uniform over the lanes of a cell)
+      if (do_bands) {
+        // the cell's secondary-ionisation factors are only needed now: loading them after the band loop keeps twelve
+        // registers free while it runs (the record's address is formed again from the cell index behind an
+        // optimisation barrier, so that only the index stays live across the loop)
+        size_t p2 = p;
+        asm volatile("" : "+l"(p2));
+        const double* rec = G.cellrec + p2 * (ISO ? CELLREC_ISO : CELLREC);
+        SecIon yR = {0, 0, 0, 0, 0, 0};
+        if (!iso) {
+          const double2 y0 = ld2(rec + 4), y1 = ld2(rec + 6), y2 = ld2(rec + 8);
+          yR.y1R0 = y0.x; yR.y1R1 = y0.y; yR.y1R2 = y1.x; yR.y2R0 = y1.y; yR.y2R1 = y2.x; yR.y2R2 = y2.y;
+        }
+        phi = photoion_finish<ISO>(A, scale, vol_ph, yR);
+        // the cell's densities again (cache hits) rather than three values held in registers across the band loop
+        const double2 d0 = ld2(rec), d1 = ld2(rec + 2);
+        phi.photo_HI = fdiv(phi.photo_HI, d0.x * (1.0 - abu_he));
+        phi.photo_HeI = fdiv(phi.photo_HeI, d0.y * abu_he);
+        phi.photo_HeII = fdiv(phi.photo_HeII, d1.x * abu_he);
       }
-      phi = photoion_finish<ISO>(A, scale, vol_ph, yR);
-      // the cell's densities again (cache hits) rather than three values held in registers across the band loop
-      const double2 d0 = ld2(rec), d1 = ld2(rec + 2);
-      phi.photo_HI = fdiv(phi.photo_HI, d0.x * (1.0 - abu_he));
-      phi.photo_HeI = fdiv(phi.photo_HeI, d0.y * abu_he);
-      phi.photo_HeII = fdiv(phi.photo_HeII, d1.x * abu_he);
     }
-    if (LANES > 1 && lane_j != 0) continue;              // one lane per cell publishes
-    atomicAdd(G.rates + p, phi.photo_HI);                // :299-306
-    atomicAdd(G.rates + G.N3 + p, phi.photo_HeI);
-    atomicAdd(G.rates + 2 * G.N3 + p, phi.photo_HeII);
-    if (!iso) atomicAdd(G.rates + 3 * G.N3 + p, phi.heat);
-    // :310-314 photon loss over the current sub-box boundary.  On the outermost shells every cell is a loss cell of
-    // one of a handful of sources: a full warp working on one source sums its contributions by shuffles first, so the
-    // per-source counter sees one atomic per warp instead of 32.
-    const bool is_loss = di == -S.lo[0] || dj == -S.lo[1] || dk == -S.lo[2] || di == S.hi[0] || dj == S.hi[1] || dk == S.hi[2];
-    if (lossbuf) {
-      lossbuf[c] = is_loss ? fdiv(phi.photo_out * d_run.vol, vol_ph) : 0.0;
-      done++;
-      continue;
-    }
-    const unsigned am = __activemask();
-    if (__any_sync(am, is_loss)) {
-      double lv = is_loss ? fdiv(phi.photo_out * d_run.vol, vol_ph) : 0.0;
-      int same = 0;
-      if (am == 0xffffffffu) __match_all_sync(am, sid, &same);
-      if (same) {
+    if (inbox && !(LANES > 1 && lane_j != 0)) {            // one lane per cell publishes
+      atomicAdd(G.rates + p, phi.photo_HI);                // :299-306
+      atomicAdd(G.rates + G.N3 + p, phi.photo_HeI);
+      atomicAdd(G.rates + 2 * G.N3 + p, phi.photo_HeII);
+      if (!iso) atomicAdd(G.rates + 3 * G.N3 + p, phi.heat);
+      // :310-314 photon loss over the current sub-box boundary.  On the outermost shells every cell is a loss cell of
+      // one of a handful of sources: a full warp working on one source sums its contributions by shuffles first, so the
+      // per-source counter sees one atomic per warp instead of 32.
+      const bool is_loss = di == -S.lo[0] || dj == -S.lo[1] || dk == -S.lo[2] || di == S.hi[0] || dj == S.hi[1] || dk == S.hi[2];
+      if (lossbuf) {
+        lossbuf[c] = is_loss ? fdiv(phi.photo_out * d_run.vol, vol_ph) : 0.0;
+      } else {
+        const unsigned am = __activemask();
+        if (__any_sync(am, is_loss)) {
+          double lv = is_loss ? fdiv(phi.photo_out * d_run.vol, vol_ph) : 0.0;
+          int same = 0;
+          if (am == 0xffffffffu) __match_all_sync(am, sid, &same);
+          if (same) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&S.loss, lv);
-      } else if (is_loss) {
-        atomicAdd(&S.loss, lv);
+            for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&S.loss, lv);
+          } else if (is_loss) {
+            atomicAdd(&S.loss, lv);
+          }
+        }
       }
+      done++;
     }
-    done++;
   }
   __syncwarp();
   done = __reduce_add_sync(0xffffffffu, done);

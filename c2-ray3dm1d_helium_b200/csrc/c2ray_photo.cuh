@@ -401,8 +401,16 @@ __device__ __forceinline__ PhotAcc photoion_bands(double in_HI, double out_HI, d
 #pragma unroll 1
     for (int s = 0; s < 3; s++) {
       const int lo = d_run.sed[s].lo, hi = d_run.sed[s].hi;
+#if C2RAY_MULTI_SCALED
+      // (warp-uniform decision, so that the band loops stay in convergent code -- k_sweep_shell; a lane whose source does
+      // not emit in this SED runs along with flux 0 and adds exact zeros)
+      const bool on = hi >= lo && nflux[s] > 0.0;
+      if (!__any_sync(0xffffffffu, on)) continue;
+      const double nf = on ? nflux[s] : 0.0;
+#else
       const double nf = nflux[s];
       if (hi < lo || !(nf > 0.0)) continue;
+#endif
       const double* __restrict__ pk = d_run.sed[s].packed;
 #if C2RAY_MULTI_SCALED
       // the SED's flux is applied inside the band step (five multiplications per band) instead of to a second set of ten
