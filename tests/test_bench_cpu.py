@@ -1,0 +1,37 @@
+"""bench.py's contract as far as it can be checked without a GPU: the reference arm (the oracle on the host's cores) prints
+exactly one line on stdout, JSON, with the keys the driver reads; everything else goes to stderr."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_reference(extra_env=None):
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                           "--mesh", "24"], capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = run_reference()
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    assert d["metric"] == "rt_source_cell_updates_per_s" and d["unit"] == "updates/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    """Under torchrun only rank 0 runs the CPU arm; the others leave with status 0 and print nothing."""
+    r = run_reference({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip() == ""
